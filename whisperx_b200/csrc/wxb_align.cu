@@ -1,0 +1,690 @@
+// libwxb_align.so — host side of the C ABI declared in include/wxb_align.h:
+// workspace, batch planner (tokens-per-lane buckets, cost sort), launch orchestration, and the
+// small kernels around the fused align_kernel (word reduction, standalone log-softmax,
+// backtrack-from-trellis).  Reference lines replaced are cited at each entry point.
+#include "../../include/wxb_align.h"
+#include "wxb_kernel.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace wxb {
+#define WXB_DECL_RANGE(lo) \
+    cudaError_t launch_range_##lo(int k, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug);
+WXB_DECL_RANGE(1) WXB_DECL_RANGE(9) WXB_DECL_RANGE(17) WXB_DECL_RANGE(25)
+WXB_DECL_RANGE(33) WXB_DECL_RANGE(41) WXB_DECL_RANGE(49) WXB_DECL_RANGE(57)
+#undef WXB_DECL_RANGE
+
+constexpr int KMAX = 64;
+constexpr int NSIDE = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+static cudaError_t launch_k(int k, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
+    switch ((k - 1) / 8) {
+        case 0: return launch_range_1(k, p, first, count, smem, st, debug);
+        case 1: return launch_range_9(k, p, first, count, smem, st, debug);
+        case 2: return launch_range_17(k, p, first, count, smem, st, debug);
+        case 3: return launch_range_25(k, p, first, count, smem, st, debug);
+        case 4: return launch_range_33(k, p, first, count, smem, st, debug);
+        case 5: return launch_range_41(k, p, first, count, smem, st, debug);
+        case 6: return launch_range_49(k, p, first, count, smem, st, debug);
+        case 7: return launch_range_57(k, p, first, count, smem, st, debug);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------ small kernels
+struct ShortSeg { long long tok_base; int N; int seg; };
+
+// Segments the planner proved un-alignable (N == 0 or N > T: column N of the trellis is -inf in
+// every row, so argmax = 0 and the walk is empty — alignment.py:396-420) get the FAILED record.
+__global__ void mark_failed_kernel(const ShortSeg *list, int n, int *status, int *nframes, int *c_start,
+                                   int *c_end, double *c_score, double *c_start_s, double *c_end_s,
+                                   double *c_score_r) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const ShortSeg s = list[i];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (threadIdx.x == 0) { status[s.seg] = WXB_SEG_FAILED; nframes[s.seg] = 0; }
+    for (int k = threadIdx.x; k < s.N; k += blockDim.x) {
+        const long long o = s.tok_base + k;
+        c_start[o] = -1; c_end[o] = -1; c_score[o] = nan;
+        if (c_start_s) { c_start_s[o] = nan; c_end_s[o] = nan; c_score_r[o] = nan; }
+    }
+}
+
+// Word reduction, alignment.py:297-320: start = min, end = max over the word's aligned chars
+// (first / last aligned char: rounded times are monotone in the frame index), score =
+// round(mean(rounded char scores), 3) with pandas' zero-filled numpy pairwise sum / count.
+__global__ void word_reduce_kernel(long long W, const int *word_seg, const long long *seg_tok_base,
+                                   const long long *wchar_off, const int *wchar_idx, const int *status,
+                                   const double *c_start_s, const double *c_end_s, const double *c_score_r,
+                                   double *w_start, double *w_end, double *w_score) {
+    const long long w = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (w >= W) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const int seg = word_seg[w];
+    const long long base = seg_tok_base[seg];
+    const long long lo = wchar_off[w];
+    const long n = static_cast<long>(wchar_off[w + 1] - lo);
+    int first = -1, last = -1;
+    long count = 0;
+    if (status[seg] == WXB_SEG_OK) {
+        for (long i = 0; i < n; ++i) {
+            const int idx = wchar_idx[lo + i];
+            if (idx >= 0) { if (first < 0) first = idx; last = idx; ++count; }
+        }
+    }
+    if (count == 0) { w_start[w] = nan; w_end[w] = nan; w_score[w] = nan; return; }
+    const double sum = pairwise_sum(
+        [&](long i) { const int idx = wchar_idx[lo + i]; return idx >= 0 ? c_score_r[base + idx] : 0.0; }, n);
+    w_start[w] = c_start_s[base + first];
+    w_end[w] = c_end_s[base + last];
+    w_score[w] = round3(sum / static_cast<double>(count));
+}
+
+// Kernel (i) on its own — torch.log_softmax(emissions, dim=-1), alignment.py:233.
+// A CTA stages `rows_per_cta` contiguous rows in shared memory with coalesced (128-bit when
+// aligned) loads, one thread per row runs the same row_lse()/logp_from() as the fused staging,
+// and the tile is written back coalesced.  HBM-bound: 8*V bytes per row.
+__global__ void __launch_bounds__(128) log_softmax_kernel(const float *in, float *out, long long rows, int V,
+                                                          int rows_per_cta) {
+    extern __shared__ __align__(16) float tile[];
+    const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+    const int nr = static_cast<int>(min(static_cast<long long>(rows_per_cta), rows - row0));
+    if (nr <= 0) return;
+    const long long base = row0 * V;
+    const int nel = nr * V;
+    const bool vec = ((reinterpret_cast<uintptr_t>(in + base) | reinterpret_cast<uintptr_t>(out + base)) & 15) == 0;
+    if (vec) {
+        const float4 *src = reinterpret_cast<const float4 *>(in + base);
+        float4 *t4 = reinterpret_cast<float4 *>(tile);
+        for (int i = threadIdx.x; i < nel / 4; i += blockDim.x) t4[i] = __ldg(src + i);
+        for (int i = (nel & ~3) + threadIdx.x; i < nel; i += blockDim.x) tile[i] = __ldg(in + base + i);
+    } else {
+        for (int i = threadIdx.x; i < nel; i += blockDim.x) tile[i] = __ldg(in + base + i);
+    }
+    __syncthreads();
+    for (int rr = threadIdx.x; rr < nr; rr += blockDim.x) {
+        float *row = tile + rr * V;
+        float m, ls;
+        row_lse([&](int v) { return row[v]; }, V, m, ls);
+        for (int v = 0; v < V; ++v) row[v] = logp_from(row[v], m, ls);
+    }
+    __syncthreads();
+    if (vec) {
+        float4 *dst = reinterpret_cast<float4 *>(out + base);
+        const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+        for (int i = threadIdx.x; i < nel / 4; i += blockDim.x) dst[i] = t4[i];
+        for (int i = (nel & ~3) + threadIdx.x; i < nel; i += blockDim.x) out[base + i] = tile[i];
+    } else {
+        for (int i = threadIdx.x; i < nel; i += blockDim.x) out[base + i] = tile[i];
+    }
+}
+
+// backtrack() from a caller-supplied trellis — the literal algorithm of alignment.py:387-421
+// (used by the functional drop-in `backtrack(trellis, emission, tokens, blank_id)`).
+__global__ void __launch_bounds__(256) backtrack_trellis_kernel(const float *R, const float *E, const int *tok,
+                                                                int T, int N, int V, int blank, int *path_tok,
+                                                                float *path_logp, int *status, int *nframes) {
+    __shared__ float s_val[256];
+    __shared__ int s_idx[256];
+    const int W = N + 1;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) { path_tok[t] = -1; path_logp[t] = 0.0f; }
+    // torch.argmax(trellis[:, N]): first maximal index, NaN counts as maximal
+    auto better = [](float av, int at, float bv, int bt) {
+        const bool an = av != av, bn = bv != bv;
+        if (an != bn) return an;
+        if (an) return at < bt;
+        return av > bv || (av == bv && at < bt);
+    };
+    float bv = R[N];
+    int bt = 0;
+    for (int t = threadIdx.x; t <= T; t += blockDim.x) {
+        const float v = R[static_cast<size_t>(t) * W + N];
+        if (better(v, t, bv, bt)) { bv = v; bt = t; }
+    }
+    s_val[threadIdx.x] = bv; s_idx[threadIdx.x] = bt;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off && better(s_val[threadIdx.x + off], s_idx[threadIdx.x + off], s_val[threadIdx.x], s_idx[threadIdx.x])) {
+            s_val[threadIdx.x] = s_val[threadIdx.x + off];
+            s_idx[threadIdx.x] = s_idx[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const int t_start = s_idx[0];
+    int j = N;
+    bool reached = false;
+    for (int t = t_start; t > 0; --t) {
+        const float *e = E + static_cast<size_t>(t - 1) * V;
+        const float stayed = R[static_cast<size_t>(t - 1) * W + j] + e[blank];
+        const float changed = R[static_cast<size_t>(t - 1) * W + j - 1] + e[tok[j - 1]];
+        const bool took = changed > stayed;
+        path_tok[t - 1] = j - 1;
+        path_logp[t - 1] = e[took ? tok[j - 1] : 0];
+        if (took) { --j; if (j == 0) { reached = true; break; } }
+    }
+    *status = reached ? WXB_SEG_OK : WXB_SEG_FAILED;
+    *nframes = t_start;
+}
+
+}  // namespace wxb
+
+using namespace wxb;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                          \
+    do {                                                                                     \
+        cudaError_t e_ = (x);                                                                \
+        if (e_ != cudaSuccess) return fail(WXB_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct wxb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t main = nullptr;              // used by wxb_align_host
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    DevBuf bits, p0, rowmax, rowlse, nframes_scratch;
+    // wxb_align_host staging
+    DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
+};
+
+struct Bucket { int K; int first; int count; long long cost; };
+
+struct wxb_plan {
+    wxb_ctx *ctx = nullptr;
+    int64_t S = 0, W = 0, sum_T = 0, sum_N = 0;
+    int V = 0, blank = 0, TE = 32;
+    uint32_t flags = 0;
+    size_t smem = 0;
+    bool has_sec = false, has_words = false;
+    std::vector<Bucket> buckets;
+    int n_short = 0;
+    long long bits_words = 0, trellis_floats = 0, cells = 0, alg_bytes = 0;
+    DevBuf d_segs, d_tokens, d_tok4, d_t1, d_ratio, d_short, d_word_seg, d_seg_tok_base, d_wchar_off, d_wchar_idx;
+    ~wxb_plan() {
+        DevBuf *all[] = {&d_segs, &d_tokens, &d_tok4, &d_t1, &d_ratio, &d_short, &d_word_seg, &d_seg_tok_base, &d_wchar_off, &d_wchar_idx};
+        for (DevBuf *b : all) b->release();
+    }
+};
+
+static int tokens_per_lane(long long n) {
+    if (n <= 0) return 0;
+    const long long k = (n + 31) / 32;
+    return k > KMAX ? -1 : static_cast<int>(k);
+}
+
+static int pick_tile(int V, int *TE, size_t *smem) {
+    // Frames per shared-memory tile.  cp.async.bulk needs 16-byte multiples, i.e. TE % 4 == 0.
+    // Prefer the longest tile whose double buffer stays <= 16 KB (28+ resident warps per SM);
+    // a wide vocabulary falls back to 8, then 4 frames per tile as long as it fits at all.
+    const int pref[3] = {32, 16, 8};
+    for (int i = 0; i < 3; ++i) {
+        const size_t bytes = 2ull * pref[i] * V * 4 + SM_TAIL_BYTES;
+        if (bytes <= 16 * 1024) { *TE = pref[i]; *smem = bytes; return 0; }
+    }
+    const int last[2] = {8, 4};
+    for (int i = 0; i < 2; ++i) {
+        const size_t bytes = 2ull * last[i] * V * 4 + SM_TAIL_BYTES;
+        if (bytes <= static_cast<size_t>(SMEM_LIMIT)) { *TE = last[i]; *smem = bytes; return 0; }
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------ ABI: lifecycle
+extern "C" int wxb_abi_version(void) { return WXB_ABI_VERSION; }
+extern "C" const char *wxb_last_error(void) { return g_err.c_str(); }
+extern "C" double wxb_round3(double x) { return wxb::round3(x); }
+extern "C" double wxb_pairwise_sum(const double *a, int64_t n) {
+    return wxb::pairwise_sum([&](long i) { return a[i]; }, static_cast<long>(n));
+}
+extern "C" int wxb_tokens_per_lane(int32_t n_tokens) { return tokens_per_lane(n_tokens); }
+
+extern "C" int wxb_create(int device, wxb_ctx **out) {
+    if (!out) return fail(WXB_EINVAL, "wxb_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(WXB_EINVAL, "wxb_create: device %d out of range (%d visible)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(WXB_EUNSUPPORTED, "wxb_create: device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", device, prop.major, prop.minor);
+    wxb_ctx *c = new (std::nothrow) wxb_ctx();
+    if (!c) return fail(WXB_ENOMEM, "wxb_create: out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
+    for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
+    if (e != cudaSuccess) {
+        wxb_destroy(c);
+        return fail(WXB_ECUDA, "wxb_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return WXB_OK;
+}
+
+extern "C" void wxb_destroy(wxb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf *bufs[] = {&c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->nframes_scratch, &c->h_emis, &c->h_path_tok};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &b : c->h_i32) b.release();
+    for (auto &b : c->h_f64) b.release();
+    for (auto &b : c->h_f32) b.release();
+    if (c->main) cudaStreamDestroy(c->main);
+    for (int i = 0; i < NSIDE; ++i) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    delete c;
+}
+
+extern "C" int wxb_get_limits(const wxb_ctx *ctx, wxb_limits *out) {
+    if (!ctx || !out) return fail(WXB_EINVAL, "wxb_get_limits: NULL argument");
+    out->max_vocab = (SMEM_LIMIT - SM_TAIL_BYTES) / (2 * 4 * 4);
+    out->max_tokens = 32 * KMAX;
+    out->tokens_per_lane = KMAX;
+    out->sm_count = ctx->sm_count;
+    return WXB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: plan
+template <class T>
+static cudaError_t upload(DevBuf &b, const T *src, size_t n) {
+    cudaError_t e = b.ensure(std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpy(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out) {
+    if (!ctx || !bt || !out) return fail(WXB_EINVAL, "wxb_plan_create: NULL argument");
+    *out = nullptr;
+    const int64_t S = bt->n_segments;
+    if (S < 0) return fail(WXB_EINVAL, "wxb_plan_create: n_segments < 0");
+    if (S > 0 && (!bt->frame_off || !bt->tok_off)) return fail(WXB_EINVAL, "wxb_plan_create: frame_off/tok_off is NULL");
+    if (bt->vocab < 1) return fail(WXB_EINVAL, "wxb_plan_create: vocab must be >= 1");
+    if (bt->blank_id < 0 || bt->blank_id >= bt->vocab) return fail(WXB_EINVAL, "wxb_plan_create: blank_id %d outside [0,%d)", bt->blank_id, bt->vocab);
+    if ((bt->seg_t1 == nullptr) != (bt->seg_ratio == nullptr)) return fail(WXB_EINVAL, "wxb_plan_create: seg_t1 and seg_ratio must be given together");
+    if (bt->n_words < 0) return fail(WXB_EINVAL, "wxb_plan_create: n_words < 0");
+    if (bt->n_words > 0 && (!bt->word_off || !bt->wchar_off || !bt->wchar_idx || !bt->seg_t1))
+        return fail(WXB_EINVAL, "wxb_plan_create: word groups need word_off, wchar_off, wchar_idx and seg_t1/seg_ratio");
+
+    wxb_plan *pl = new (std::nothrow) wxb_plan();
+    if (!pl) return fail(WXB_ENOMEM, "wxb_plan_create: out of host memory");
+    struct Guard { wxb_plan *p; ~Guard() { delete p; } } guard{pl};
+    pl->ctx = ctx;
+    pl->S = S;
+    pl->V = bt->vocab;
+    pl->blank = bt->blank_id;
+    pl->flags = bt->flags;
+    pl->has_sec = bt->seg_t1 != nullptr;
+    pl->W = bt->n_words;
+    pl->has_words = bt->n_words > 0;
+    if (pick_tile(pl->V, &pl->TE, &pl->smem) != 0)
+        return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory per tile", pl->V, SMEM_LIMIT);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (S == 0) { guard.p = nullptr; *out = pl; return WXB_OK; }
+
+    const int64_t *fo = bt->frame_off, *to = bt->tok_off;
+    if (fo[0] < 0 || to[0] < 0) return fail(WXB_EINVAL, "wxb_plan_create: negative offset");
+    for (int64_t s = 0; s < S; ++s) {
+        if (fo[s + 1] < fo[s] || to[s + 1] < to[s]) return fail(WXB_EINVAL, "wxb_plan_create: offsets not ascending at segment %lld", (long long)s);
+        if (fo[s + 1] - fo[s] > 0x3fffffff || to[s + 1] - to[s] > 0x3fffffff) return fail(WXB_EINVAL, "wxb_plan_create: segment %lld too large", (long long)s);
+        if (bt->frame_len && (bt->frame_len[s] < 0 || bt->frame_len[s] > fo[s + 1] - fo[s]))
+            return fail(WXB_EINVAL, "wxb_plan_create: frame_len[%lld]=%d outside [0,%lld]", (long long)s, bt->frame_len[s], (long long)(fo[s + 1] - fo[s]));
+    }
+    pl->sum_T = fo[S];
+    pl->sum_N = to[S];
+    if (pl->sum_N > 0 && !bt->tokens) return fail(WXB_EINVAL, "wxb_plan_create: tokens is NULL");
+    for (int64_t i = to[0]; i < to[S]; ++i)
+        if (bt->tokens[i] < 0 || bt->tokens[i] >= pl->V) return fail(WXB_EINVAL, "wxb_plan_create: tokens[%lld]=%d outside [0,%d)", (long long)i, bt->tokens[i], pl->V);
+
+    // ---- bucket by tokens-per-lane, shortcut provably failing segments ----
+    std::vector<SegDesc> descs;
+    descs.reserve(static_cast<size_t>(S));
+    std::vector<ShortSeg> shorts;
+    std::vector<long long> seg_tok_base(static_cast<size_t>(S));
+    long long trellis_off = 0;
+    const bool no_shortcut = (bt->flags & WXB_F_NO_SHORTCUT) != 0;
+    for (int64_t s = 0; s < S; ++s) {
+        const int T = bt->frame_len ? bt->frame_len[s] : static_cast<int>(fo[s + 1] - fo[s]);
+        const int N = static_cast<int>(to[s + 1] - to[s]);
+        seg_tok_base[s] = to[s];
+        const long long this_trellis = trellis_off;
+        trellis_off += static_cast<long long>(T + 1) * (N + 1);
+        const int K = tokens_per_lane(N);
+        if (N == 0 || (N > T && (!no_shortcut || K < 0))) {
+            shorts.push_back({to[s], N, static_cast<int>(s)});
+            continue;
+        }
+        if (K < 0)
+            return fail(WXB_EUNSUPPORTED, "wxb_plan_create: segment %lld has %d tokens; this build aligns at most %d per segment", (long long)s, N, 32 * KMAX);
+        SegDesc d;
+        d.emis_off = fo[s] * static_cast<long long>(pl->V);
+        d.frame_base = fo[s];
+        d.tok_base = to[s];
+        d.bits_off = 0;
+        d.trellis_off = this_trellis;
+        d.T = T; d.N = N; d.seg = static_cast<int>(s); d.K = K;
+        descs.push_back(d);
+        pl->cells += static_cast<long long>(T) * N;
+        pl->alg_bytes += 4ll * T * pl->V + 20ll * N;
+    }
+    pl->trellis_floats = trellis_off;
+    pl->n_short = static_cast<int>(shorts.size());
+    // longest-first inside a bucket: the block scheduler hands out CTAs in index order (LPT)
+    std::stable_sort(descs.begin(), descs.end(), [](const SegDesc &a, const SegDesc &b) {
+        if (a.K != b.K) return a.K > b.K;
+        return a.T > b.T;
+    });
+    long long bits = 0;
+    for (size_t i = 0; i < descs.size(); ++i) {
+        descs[i].bits_off = bits;
+        bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].K * 32;
+        if (i == 0 || descs[i].K != descs[i - 1].K) pl->buckets.push_back({descs[i].K, static_cast<int>(i), 0, 0});
+        pl->buckets.back().count += 1;
+        pl->buckets.back().cost += static_cast<long long>(descs[i].T) * descs[i].K;
+    }
+    pl->bits_words = bits;
+    std::stable_sort(pl->buckets.begin(), pl->buckets.end(), [](const Bucket &a, const Bucket &b) { return a.cost > b.cost; });
+
+    // ---- upload ----
+    std::vector<int> tok4(static_cast<size_t>(std::max<int64_t>(pl->sum_N, 1)));
+    for (int64_t i = 0; i < pl->sum_N; ++i) tok4[i] = bt->tokens[i] * 4;
+    CUDA_TRY(upload(pl->d_segs, descs.data(), descs.size()));
+    CUDA_TRY(upload(pl->d_tokens, bt->tokens, static_cast<size_t>(pl->sum_N)));
+    CUDA_TRY(upload(pl->d_tok4, tok4.data(), static_cast<size_t>(pl->sum_N)));
+    CUDA_TRY(upload(pl->d_short, shorts.data(), shorts.size()));
+    if (pl->has_sec) {
+        CUDA_TRY(upload(pl->d_t1, bt->seg_t1, static_cast<size_t>(S)));
+        CUDA_TRY(upload(pl->d_ratio, bt->seg_ratio, static_cast<size_t>(S)));
+    }
+    if (pl->has_words) {
+        const int64_t W = pl->W;
+        if (bt->word_off[0] != 0 || bt->word_off[S] != W) return fail(WXB_EINVAL, "wxb_plan_create: word_off must run from 0 to n_words");
+        std::vector<int> word_seg(static_cast<size_t>(W));
+        for (int64_t s = 0; s < S; ++s) {
+            if (bt->word_off[s + 1] < bt->word_off[s]) return fail(WXB_EINVAL, "wxb_plan_create: word_off not ascending");
+            for (int64_t w = bt->word_off[s]; w < bt->word_off[s + 1]; ++w) word_seg[w] = static_cast<int>(s);
+        }
+        for (int64_t w = 0; w < W; ++w) {
+            if (bt->wchar_off[w + 1] < bt->wchar_off[w]) return fail(WXB_EINVAL, "wxb_plan_create: wchar_off not ascending");
+            const int N = static_cast<int>(to[word_seg[w] + 1] - to[word_seg[w]]);
+            for (int64_t i = bt->wchar_off[w]; i < bt->wchar_off[w + 1]; ++i)
+                if (bt->wchar_idx[i] < -1 || bt->wchar_idx[i] >= N) return fail(WXB_EINVAL, "wxb_plan_create: wchar_idx[%lld]=%d outside [-1,%d)", (long long)i, bt->wchar_idx[i], N);
+        }
+        CUDA_TRY(upload(pl->d_word_seg, word_seg.data(), word_seg.size()));
+        CUDA_TRY(upload(pl->d_seg_tok_base, seg_tok_base.data(), seg_tok_base.size()));
+        CUDA_TRY(upload(pl->d_wchar_off, bt->wchar_off, static_cast<size_t>(W + 1)));
+        CUDA_TRY(upload(pl->d_wchar_idx, bt->wchar_idx, static_cast<size_t>(bt->wchar_off[W])));
+    }
+    guard.p = nullptr;
+    *out = pl;
+    return WXB_OK;
+}
+
+extern "C" void wxb_plan_destroy(wxb_plan *plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    delete plan;
+}
+
+extern "C" int wxb_plan_launch_count(const wxb_plan *plan) {
+    if (!plan) return 0;
+    return static_cast<int>(plan->buckets.size()) + (plan->n_short > 0 ? 1 : 0) + (plan->has_words ? 1 : 0);
+}
+
+extern "C" int wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg_bytes, int64_t *n_shortcut) {
+    if (!plan) return fail(WXB_EINVAL, "wxb_plan_stats: plan is NULL");
+    if (cells) *cells = plan->cells;
+    if (alg_bytes) *alg_bytes = plan->alg_bytes;
+    if (n_shortcut) *n_shortcut = plan->n_short;
+    return WXB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: run
+extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *o, void *stream_, float *elapsed_dp_ms) {
+    if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
+    if (pl->S == 0) { if (elapsed_dp_ms) *elapsed_dp_ms = 0.f; return WXB_OK; }
+    if (!o->status || !o->char_start || !o->char_end || !o->char_score)
+        return fail(WXB_EINVAL, "wxb_plan_run: status, char_start, char_end and char_score are required outputs");
+    if (!emis && pl->sum_T > 0) return fail(WXB_EINVAL, "wxb_plan_run: emissions is NULL");
+    if ((o->path_token == nullptr) != (o->path_logp == nullptr)) return fail(WXB_EINVAL, "wxb_plan_run: path_token and path_logp go together");
+    const bool want_sec = o->char_start_s || o->char_end_s || o->char_score_r;
+    if (want_sec && !(o->char_start_s && o->char_end_s && o->char_score_r && pl->has_sec))
+        return fail(WXB_EINVAL, "wxb_plan_run: second-valued outputs need all three char_*_s/_r buffers and seg_t1/seg_ratio in the batch");
+    const bool want_words = o->word_start_s || o->word_end_s || o->word_score;
+    if (want_words && !(o->word_start_s && o->word_end_s && o->word_score && pl->has_words && want_sec))
+        return fail(WXB_EINVAL, "wxb_plan_run: word outputs need all three word buffers, word groups in the batch and the char_*_s outputs");
+    const bool logits = (pl->flags & WXB_F_LOGITS) != 0;
+    if (o->logprobs && !logits) return fail(WXB_EINVAL, "wxb_plan_run: logprobs output is only produced with WXB_F_LOGITS");
+    const bool debug = o->trellis || o->final_col;
+
+    wxb_ctx *c = pl->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    CUDA_TRY(c->bits.ensure(static_cast<size_t>(std::max<long long>(pl->bits_words, 1)) * 4));
+    CUDA_TRY(c->p0.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+    if (logits) {
+        CUDA_TRY(c->rowmax.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+        CUDA_TRY(c->rowlse.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+    }
+    int *nframes = o->n_frames;
+    if (!nframes) {
+        CUDA_TRY(c->nframes_scratch.ensure(static_cast<size_t>(pl->S) * 4));
+        nframes = c->nframes_scratch.as<int>();
+    }
+
+    Params P;
+    memset(&P, 0, sizeof P);
+    P.emis = emis;
+    P.tokens = pl->d_tokens.as<int>();
+    P.tok4 = pl->d_tok4.as<int>();
+    P.segs = pl->d_segs.as<SegDesc>();
+    P.bits = c->bits.as<uint32_t>();
+    P.p0 = c->p0.as<float>();
+    P.rowmax = c->rowmax.as<float>();
+    P.rowlse = c->rowlse.as<float>();
+    P.V = pl->V; P.blank = pl->blank; P.TE = pl->TE; P.is_logits = logits ? 1 : 0;
+    P.status = o->status; P.nframes = nframes;
+    P.c_start = o->char_start; P.c_end = o->char_end; P.c_score = o->char_score;
+    if (want_sec) {
+        P.c_start_s = o->char_start_s; P.c_end_s = o->char_end_s; P.c_score_r = o->char_score_r;
+        P.seg_t1 = pl->d_t1.as<double>(); P.seg_ratio = pl->d_ratio.as<double>();
+    }
+    P.path_tok = o->path_token; P.path_logp = o->path_logp;
+    P.final_col = o->final_col; P.trellis = o->trellis; P.logprobs = o->logprobs;
+
+    if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t0, st));
+    const int nb = static_cast<int>(pl->buckets.size());
+    if (nb == 1) {
+        const Bucket &b = pl->buckets[0];
+        CUDA_TRY(launch_k(b.K, P, b.first, b.count, pl->smem, st, debug));
+    } else if (nb > 1) {
+        // buckets are independent: fork onto side streams so that every SM sees a mix of K classes
+        const int used = std::min(nb, NSIDE);
+        CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+        for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+        for (int i = 0; i < nb; ++i) {
+            const Bucket &b = pl->buckets[i];
+            CUDA_TRY(launch_k(b.K, P, b.first, b.count, pl->smem, c->side[i % used], debug));
+        }
+        for (int i = 0; i < used; ++i) {
+            CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));
+            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[i], 0));
+        }
+    }
+    if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t1, st));
+    if (pl->n_short > 0) {
+        mark_failed_kernel<<<pl->n_short, 64, 0, st>>>(pl->d_short.as<ShortSeg>(), pl->n_short, o->status, nframes,
+                                                        o->char_start, o->char_end, o->char_score,
+                                                        want_sec ? o->char_start_s : nullptr, o->char_end_s, o->char_score_r);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (want_words) {
+        const int threads = 128;
+        const long long blocks = (pl->W + threads - 1) / threads;
+        word_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+            pl->W, pl->d_word_seg.as<int>(), pl->d_seg_tok_base.as<long long>(), pl->d_wchar_off.as<long long>(),
+            pl->d_wchar_idx.as<int>(), o->status, o->char_start_s, o->char_end_s, o->char_score_r,
+            o->word_start_s, o->word_end_s, o->word_score);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (elapsed_dp_ms) {
+        CUDA_TRY(cudaEventSynchronize(c->ev_t1));
+        CUDA_TRY(cudaEventElapsedTime(elapsed_dp_ms, c->ev_t0, c->ev_t1));
+    }
+    return WXB_OK;
+}
+
+extern "C" int wxb_align_device(wxb_ctx *ctx, const wxb_batch *batch, const float *emissions_dev,
+                                const wxb_outputs *out_dev, void *stream) {
+    wxb_plan *pl = nullptr;
+    int rc = wxb_plan_create(ctx, batch, &pl);
+    if (rc != WXB_OK) return rc;
+    rc = wxb_plan_run(pl, emissions_dev, out_dev, stream, nullptr);
+    if (rc == WXB_OK) {
+        // the plan's device arrays must outlive the kernels that read them
+        cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) rc = fail(WXB_ECUDA, "wxb_align_device: %s", cudaGetErrorString(e));
+    }
+    wxb_plan_destroy(pl);
+    return rc;
+}
+
+extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis_host, const wxb_outputs *oh) {
+    if (!c || !bt || !oh) return fail(WXB_EINVAL, "wxb_align_host: NULL argument");
+    wxb_plan *pl = nullptr;
+    int rc = wxb_plan_create(c, bt, &pl);
+    if (rc != WXB_OK) return rc;
+    struct Guard { wxb_plan *p; ~Guard() { wxb_plan_destroy(p); } } guard{pl};
+    if (pl->S == 0) return WXB_OK;
+    const size_t S = static_cast<size_t>(pl->S), sN = static_cast<size_t>(std::max<int64_t>(pl->sum_N, 1));
+    const size_t sT = static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)), W = static_cast<size_t>(std::max<int64_t>(pl->W, 1));
+    const size_t V = static_cast<size_t>(pl->V);
+    wxb_outputs od;
+    memset(&od, 0, sizeof od);
+    CUDA_TRY(c->h_emis.ensure(sT * V * 4));
+    CUDA_TRY(c->h_i32[0].ensure(S * 4)); od.status = c->h_i32[0].as<int32_t>();
+    CUDA_TRY(c->h_i32[1].ensure(S * 4)); od.n_frames = c->h_i32[1].as<int32_t>();
+    CUDA_TRY(c->h_i32[2].ensure(sN * 4)); od.char_start = c->h_i32[2].as<int32_t>();
+    CUDA_TRY(c->h_i32[3].ensure(sN * 4)); od.char_end = c->h_i32[3].as<int32_t>();
+    CUDA_TRY(c->h_f64[0].ensure(sN * 8)); od.char_score = c->h_f64[0].as<double>();
+    const bool want_sec = oh->char_start_s || oh->char_end_s || oh->char_score_r || oh->word_start_s;
+    if (want_sec) {
+        CUDA_TRY(c->h_f64[1].ensure(sN * 8)); od.char_start_s = c->h_f64[1].as<double>();
+        CUDA_TRY(c->h_f64[2].ensure(sN * 8)); od.char_end_s = c->h_f64[2].as<double>();
+        CUDA_TRY(c->h_f64[3].ensure(sN * 8)); od.char_score_r = c->h_f64[3].as<double>();
+    }
+    if (oh->word_start_s || oh->word_end_s || oh->word_score) {
+        CUDA_TRY(c->h_f64[4].ensure(W * 8)); od.word_start_s = c->h_f64[4].as<double>();
+        CUDA_TRY(c->h_f64[5].ensure(W * 8)); od.word_end_s = c->h_f64[5].as<double>();
+        CUDA_TRY(c->h_f64[6].ensure(W * 8)); od.word_score = c->h_f64[6].as<double>();
+    }
+    if (oh->path_token) {
+        CUDA_TRY(c->h_path_tok.ensure(sT * 4)); od.path_token = c->h_path_tok.as<int32_t>();
+        CUDA_TRY(c->h_f32[0].ensure(sT * 4)); od.path_logp = c->h_f32[0].as<float>();
+    }
+    if (oh->final_col) { CUDA_TRY(c->h_f32[1].ensure((sT + S) * 4)); od.final_col = c->h_f32[1].as<float>(); }
+    if (oh->trellis) { CUDA_TRY(c->h_f32[2].ensure(static_cast<size_t>(std::max<long long>(pl->trellis_floats, 1)) * 4)); od.trellis = c->h_f32[2].as<float>(); }
+    if (oh->logprobs) { CUDA_TRY(c->h_f32[3].ensure(sT * V * 4)); od.logprobs = c->h_f32[3].as<float>(); }
+
+    cudaStream_t st = c->main;
+    if (pl->sum_T > 0) CUDA_TRY(cudaMemcpyAsync(c->h_emis.p, emis_host, static_cast<size_t>(pl->sum_T) * V * 4, cudaMemcpyHostToDevice, st));
+    rc = wxb_plan_run(pl, c->h_emis.as<float>(), &od, st, nullptr);
+    if (rc != WXB_OK) return rc;
+#define WXB_D2H(field, count, type)                                                                   \
+    if (oh->field && (count) > 0)                                                                     \
+        CUDA_TRY(cudaMemcpyAsync(oh->field, od.field, static_cast<size_t>(count) * sizeof(type), cudaMemcpyDeviceToHost, st));
+    WXB_D2H(status, pl->S, int32_t) WXB_D2H(n_frames, pl->S, int32_t)
+    WXB_D2H(char_start, pl->sum_N, int32_t) WXB_D2H(char_end, pl->sum_N, int32_t) WXB_D2H(char_score, pl->sum_N, double)
+    WXB_D2H(char_start_s, pl->sum_N, double) WXB_D2H(char_end_s, pl->sum_N, double) WXB_D2H(char_score_r, pl->sum_N, double)
+    WXB_D2H(word_start_s, pl->W, double) WXB_D2H(word_end_s, pl->W, double) WXB_D2H(word_score, pl->W, double)
+    WXB_D2H(path_token, pl->sum_T, int32_t) WXB_D2H(path_logp, pl->sum_T, float)
+    WXB_D2H(final_col, pl->sum_T + pl->S, float) WXB_D2H(trellis, pl->trellis_floats, float)
+    WXB_D2H(logprobs, pl->sum_T * pl->V, float)
+#undef WXB_D2H
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return WXB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: stand-alone kernels
+extern "C" int wxb_log_softmax_device(wxb_ctx *ctx, const float *logits_dev, int64_t rows, int32_t vocab,
+                                      float *out_dev, void *stream) {
+    if (!ctx || (rows > 0 && (!logits_dev || !out_dev))) return fail(WXB_EINVAL, "wxb_log_softmax_device: NULL argument");
+    if (rows < 0 || vocab < 1) return fail(WXB_EINVAL, "wxb_log_softmax_device: bad shape");
+    if (rows == 0) return WXB_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t row_bytes = static_cast<size_t>(vocab) * 4;
+    if (row_bytes > static_cast<size_t>(SMEM_LIMIT)) return fail(WXB_EUNSUPPORTED, "wxb_log_softmax_device: vocab %d too large", vocab);
+    int rpc = static_cast<int>(std::min<size_t>(128, (40 * 1024) / row_bytes));
+    if (rpc >= 4) rpc &= ~3;
+    if (rpc < 1) rpc = 1;
+    const size_t smem = static_cast<size_t>(rpc) * row_bytes;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(log_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const long long blocks = (rows + rpc - 1) / rpc;
+    log_softmax_kernel<<<static_cast<unsigned>(blocks), 128, smem, static_cast<cudaStream_t>(stream)>>>(logits_dev, out_dev, rows, vocab, rpc);
+    CUDA_TRY(cudaGetLastError());
+    return WXB_OK;
+}
+
+extern "C" int wxb_backtrack_trellis_device(wxb_ctx *ctx, const float *trellis_dev, const float *emission_dev,
+                                            const int32_t *tokens_dev, int32_t T, int32_t N, int32_t vocab,
+                                            int32_t blank_id, int32_t *path_token_dev, float *path_logp_dev,
+                                            int32_t *status_dev, int32_t *n_frames_dev, void *stream) {
+    if (!ctx || !trellis_dev || !emission_dev || !tokens_dev || !path_token_dev || !path_logp_dev || !status_dev || !n_frames_dev)
+        return fail(WXB_EINVAL, "wxb_backtrack_trellis_device: NULL argument");
+    if (T < 0 || N < 1 || vocab < 1 || blank_id < 0 || blank_id >= vocab)
+        return fail(WXB_EINVAL, "wxb_backtrack_trellis_device: bad shape (T=%d N=%d V=%d blank=%d)", T, N, vocab, blank_id);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    backtrack_trellis_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(trellis_dev, emission_dev, tokens_dev, T, N, vocab,
+                                                                              blank_id, path_token_dev, path_logp_dev,
+                                                                              status_dev, n_frames_dev);
+    CUDA_TRY(cudaGetLastError());
+    return WXB_OK;
+}
