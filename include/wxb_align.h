@@ -64,6 +64,10 @@ typedef struct wxb_batch {
      * Both NULL -> the *_s / *_r / word outputs are not produced. */
     const double  *seg_t1;       /* [S] segment start time t1 (alignment.py:184) */
     const double  *seg_ratio;    /* [S] duration/T as the reference computes it (alignment.py:253) */
+    const uint8_t *seg_round_np; /* [S] or NULL.  1: the segment's start/end were numpy scalars in the caller, so
+                                    `frame*ratio + t1` is a np.float64 and round(.,3) is numpy's rint(x*1000)/1000;
+                                    0 / NULL: Python float rounding (exact decimal, half-even).  Scores: char scores
+                                    always round the Python way (:264), word scores always the numpy way (:308). */
     /* Optional word groups (alignment.py:297-320): word w of the batch owns entries
      * wchar_off[w] .. wchar_off[w+1] of wchar_idx; segment s owns words word_off[s] .. word_off[s+1].
      * wchar_idx holds, for each non-space character of the word in text order, the index of its
@@ -154,8 +158,14 @@ int  wxb_backtrack_trellis_device(wxb_ctx *ctx, const float *trellis_dev, const 
                                   int32_t blank_id, int32_t *path_token_dev, float *path_logp_dev,
                                   int32_t *status_dev, int32_t *n_frames_dev, void *stream);
 
+/* ---- debug aid: per-CTA timeline of the last wxb_plan_run (ctx created with env WXB_TRACE=1) ----
+ * rows: [cap_rows][8] = {t_begin_ns, t_forward_done_ns, t_end_ns, smid, T, N, K, segment}; returns the
+ * number of rows written or a negative error code. */
+int  wxb_plan_debug_trace(wxb_plan *plan, uint64_t *rows, int64_t cap_rows);
+
 /* ---- host-side exact helpers (no GPU needed; the device code uses the same source) ---- */
 double wxb_round3(double x);                              /* Python round(x, 3) (alignment.py:262-264) */
+double wxb_round3_np(double x);                           /* np.float64.__round__(3) (alignment.py:308) */
 double wxb_pairwise_sum(const double *a, int64_t n);      /* numpy add.reduce order (alignment.py:308) */
 int    wxb_tokens_per_lane(int32_t n_tokens);             /* K bucket for N tokens, <=0 if unsupported */
 

@@ -180,6 +180,10 @@ double wxo_round3(double x) {
     return strtod(buf, NULL);
 }
 
+/* round(x, 3) on a numpy float64 scalar (np.float64.__round__ == np.round: scale, rint, unscale);
+ * this is what `round(word_chars["score"].mean(), 3)` evaluates (alignment.py:308). */
+double wxo_round3_np(double x) { return rint(x * 1000.0) / 1000.0; }
+
 /* numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE),
  * as reached by pandas nanmean -> ndarray.sum() on a contiguous float64 vector. */
 static double pw(const double *a, long n) {

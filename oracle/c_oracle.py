@@ -38,6 +38,8 @@ def lib():
         L.wxo_align_segment.restype = C.c_int
         L.wxo_round3.argtypes = [C.c_double]
         L.wxo_round3.restype = C.c_double
+        L.wxo_round3_np.argtypes = [C.c_double]
+        L.wxo_round3_np.restype = C.c_double
         L.wxo_pairwise_sum.argtypes = [f64p, C.c_long]
         L.wxo_pairwise_sum.restype = C.c_double
         L.wxo_align_batch.argtypes = [f32p, i64p, i32p, i64p, C.c_long, C.c_int, C.c_int,
@@ -115,6 +117,10 @@ def align_batch(E, frame_off, tokens, tok_off, V: int, blank: int = 0):
 
 def round3(x: float) -> float:
     return lib().wxo_round3(float(x))
+
+
+def round3_np(x: float) -> float:
+    return lib().wxo_round3_np(float(x))
 
 
 def pairwise_sum(a) -> float:

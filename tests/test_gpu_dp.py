@@ -1,0 +1,306 @@
+"""GPU: the CUDA engine against the oracle through the C ABI — bit-exact trellis / final column /
+paths / frame indices, scores within 1e-6 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from tests.helpers import concat_cases, logprobs
+from whisperx_b200 import synth
+from whisperx_b200.engine import BatchSpec
+
+pytestmark = pytest.mark.gpu
+SCORE_RTOL = 1e-6          # north_star: per-char scores within 1e-6 relative
+
+
+def run(engine, cases, V, blank, align=1, want=("path", "final_col", "trellis"), host=False, **kw):
+    E, fo, fl, to, tok = concat_cases(cases, V, align)
+    spec = BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank, **kw)
+    if host:
+        res = engine.align_batch_host(E, spec, want=want)
+    else:
+        res = engine.align_batch(torch.from_numpy(E).cuda(), spec, want=want).cpu()
+    return spec, res
+
+
+def check_against_oracle(spec, res, cases, blank, full=True):
+    fo, to = spec.frame_off, spec.tok_off
+    troff = spec.trellis_offsets()
+    for s, (E, tk) in enumerate(cases):
+        T, N = E.shape[0], len(tk)
+        rc, cs, ce, sc, ts = c_oracle.align_segment(E, tk, blank)
+        assert int(res.status[s]) == rc, (s, T, N)
+        sl = slice(int(to[s]), int(to[s + 1]))
+        if rc == 0:
+            assert np.array_equal(res.char_start[sl].numpy(), cs), (s, T, N)
+            assert np.array_equal(res.char_end[sl].numpy(), ce), (s, T, N)
+            np.testing.assert_allclose(res.char_score[sl].numpy(), sc, rtol=SCORE_RTOL, atol=0)
+            assert int(res.n_frames[s]) == ts
+        else:
+            assert int(res.n_frames[s]) == 0
+            assert (res.char_start[sl] == -1).all() and torch.isnan(res.char_score[sl]).all()
+        if not full:
+            continue
+        R = c_oracle.forward_trellis(E, tk, blank)
+        if res.trellis is not None:
+            Rg = res.trellis[troff[s]:troff[s + 1]].numpy().reshape(T + 1, N + 1)
+            assert np.array_equal(Rg.view(np.int32), R.view(np.int32)), (s, T, N)
+        if res.final_col is not None:
+            fc = res.final_col[fo[s] + s: fo[s] + s + T + 1].numpy()
+            assert np.array_equal(fc.view(np.int32), R[:, N].view(np.int32))
+        if res.path_token is not None:
+            pt = res.path_token[fo[s]:fo[s] + T].numpy()
+            pl = res.path_logp[fo[s]:fo[s] + T].numpy()
+            p = c_oracle.walk_back(R, E, tk, blank)
+            if p is None:
+                assert (pt == -1).all()
+            else:
+                on = np.nonzero(pt >= 0)[0]
+                assert on.tolist() == p["time"].tolist()
+                assert pt[on].tolist() == p["tok"].tolist()
+                assert np.array_equal(pl[on].view(np.int32), p["logp"].view(np.int32))   # bit-exact log-probs
+
+
+@pytest.mark.parametrize("V,blank,align", [(29, 0, 1), (29, 0, 4), (29, 7, 4), (100, 99, 1), (100, 99, 4), (5, 2, 1), (2, 1, 4)])
+def test_random_segments_bit_exact(engine, V, blank, align):
+    rng = np.random.default_rng(100 + V + align)
+    cases = []
+    for c in range(150):
+        T = int(rng.integers(1, 160))
+        N = int(rng.integers(1, T + 1)) if c % 5 else int(rng.integers(1, T + 4))
+        cases.append((logprobs(rng, T, V, ties=(c % 3 == 1)), rng.integers(0, V, N).astype(np.int32)))
+    spec, res = run(engine, cases, V, blank, align, no_shortcut=True)
+    check_against_oracle(spec, res, cases, blank)
+
+
+def test_golden_reference_vectors(engine, golden_dp):
+    """Committed outputs of the real reference (tests/golden/dp_cases.*)."""
+    meta, arr = golden_dp
+    for V, blank in ((29, 0), (7, 3)):
+        ms = [m for m in meta if m["V"] == V and m["blank"] == blank]
+        cases = [(arr[m["name"] + "_E"], arr[m["name"] + "_tok"]) for m in ms]
+        spec, res = run(engine, cases, V, blank, no_shortcut=True)
+        troff = spec.trellis_offsets()
+        for s, m in enumerate(ms):
+            n = m["name"]
+            T, N = m["T"], m["N"]
+            Rg = res.trellis[troff[s]:troff[s + 1]].numpy().reshape(T + 1, N + 1)
+            assert np.array_equal(Rg.view(np.int32), arr[n + "_R"].view(np.int32)), m
+            assert int(res.status[s]) == (0 if m["ok"] else 1), m
+            if not m["ok"]:
+                continue
+            sl = slice(int(spec.tok_off[s]), int(spec.tok_off[s + 1]))
+            assert res.char_start[sl].tolist() == arr[n + "_sstart"].tolist(), m
+            assert res.char_end[sl].tolist() == arr[n + "_send"].tolist(), m
+            np.testing.assert_allclose(res.char_score[sl].numpy(), arr[n + "_sscore"], rtol=SCORE_RTOL, atol=0)
+            pt = res.path_token[spec.frame_off[s]:spec.frame_off[s] + T].numpy()
+            on = np.nonzero(pt >= 0)[0]
+            assert on.tolist() == arr[n + "_ptime"].tolist() and pt[on].tolist() == arr[n + "_ptok"].tolist()
+            pl = res.path_logp[spec.frame_off[s]:spec.frame_off[s] + T][on]
+            # exp of the engine's path log-probs with torch CPU == the reference's Point.score, bit for bit
+            assert torch.exp(pl).double().tolist() == arr[n + "_pscore"].tolist()
+
+
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 64, 65, 95, 97, 416, 417, 512, 513, 700, 1023, 1025, 1500, 2047, 2048])
+def test_every_token_bucket_boundary(engine, N):
+    """tokens-per-lane classes K=1..64 incl. the r=1 / r=32 lane splits."""
+    rng = np.random.default_rng(N)
+    T = N + int(rng.integers(0, 120))
+    cases = [(logprobs(rng, T, 29, ties=bool(N % 2)), rng.integers(0, 29, N).astype(np.int32))]
+    small = N <= 700
+    spec, res = run(engine, cases, 29, 0, align=4, want=("path", "final_col", "trellis") if small else ("path",))
+    check_against_oracle(spec, res, cases, 0, full=small)
+
+
+def test_all_K_classes_one_batch(engine):
+    rng = np.random.default_rng(9)
+    cases = []
+    for K in range(1, 65):
+        N = 32 * (K - 1) + int(rng.integers(1, 33))
+        T = N + int(rng.integers(0, 40))
+        cases.append((logprobs(rng, T, 29), rng.integers(0, 29, N).astype(np.int32)))
+    spec, res = run(engine, cases, 29, 0, align=4, want=())
+    check_against_oracle(spec, res, cases, 0, full=False)
+
+
+def test_edge_shapes_and_failures(engine):
+    rng = np.random.default_rng(4)
+    V = 29
+    cases = []
+    for T, N in ((1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 5), (40, 40), (40, 41), (40, 39), (33, 1), (0, 3), (5, 0)):
+        cases.append((logprobs(rng, T, V) if T else np.zeros((0, V), np.float32), rng.integers(0, V, N).astype(np.int32)))
+    # with the host shortcut (default) and with the kernel deciding on its own
+    for no_shortcut in (False, True):
+        runnable = [c for c in cases if not (no_shortcut and (c[0].shape[0] == 0 or len(c[1]) == 0))] if no_shortcut else cases
+        spec, res = run(engine, runnable, V, 0, want=("path",), no_shortcut=no_shortcut)
+        for s, (E, tk) in enumerate(runnable):
+            T, N = E.shape[0], len(tk)
+            if N == 0 or T == 0:
+                assert int(res.status[s]) == 1
+                continue
+            rc, cs, ce, sc, ts = c_oracle.align_segment(E, tk, 0)
+            assert int(res.status[s]) == rc, (T, N, no_shortcut)
+            if rc == 0:
+                sl = slice(int(spec.tok_off[s]), int(spec.tok_off[s + 1]))
+                assert res.char_start[sl].tolist() == cs.tolist() and res.char_end[sl].tolist() == ce.tolist()
+
+
+def test_empty_batch(engine):
+    spec = BatchSpec(frame_off=np.zeros(1, np.int64), tok_off=np.zeros(1, np.int64), tokens=np.zeros(0, np.int32), vocab=29)
+    res = engine.align_batch(torch.zeros((0, 29), device="cuda"), spec)
+    assert res.status.numel() >= 0
+
+
+def test_invalid_arguments_raise(engine):
+    from whisperx_b200._native import NativeError
+    E = torch.zeros((4, 29), device="cuda")
+    with pytest.raises(NativeError):
+        engine.align_batch(E, BatchSpec(frame_off=[0, 4], tok_off=[0, 2], tokens=[1, 29], vocab=29))      # token out of range
+    with pytest.raises(NativeError):
+        engine.align_batch(E, BatchSpec(frame_off=[0, 4], tok_off=[0, 2], tokens=[1, 2], vocab=29, blank_id=29))
+    with pytest.raises(NativeError):
+        engine.align_batch(E, BatchSpec(frame_off=[4, 0], tok_off=[0, 2], tokens=[1, 2], vocab=29))
+    with pytest.raises(ValueError):
+        engine.align_batch(torch.zeros((2, 29), device="cuda"), BatchSpec(frame_off=[0, 4], tok_off=[0, 2], tokens=[1, 2], vocab=29))
+
+
+def test_logits_mode_is_path_exact_on_own_logprobs(engine):
+    """Fused log-softmax: feeding the engine's own log-probs to the oracle DP reproduces its paths
+    exactly, and those log-probs are within 2 ulp-ish of torch's (SURVEY §7.2 hard part 1)."""
+    rng = np.random.default_rng(21)
+    for V, blank in ((29, 0), (100, 99), (33, 4)):
+        raw, toks = [], []
+        for c in range(60):
+            T = int(rng.integers(2, 300)); N = int(rng.integers(1, T + 1))
+            raw.append(rng.standard_normal((T, V)).astype(np.float32) * 3)
+            toks.append(rng.integers(0, V, N).astype(np.int32))
+        for align in (1, 4):
+            E, fo, fl, to, tok = concat_cases(list(zip(raw, toks)), V, align)
+            spec = BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank, logits=True)
+            res = engine.align_batch(torch.from_numpy(E).cuda(), spec, want=("path", "logprobs")).cpu()
+            lp = res.logprobs.view(-1, V).numpy()
+            alone = engine.log_softmax(torch.from_numpy(E).cuda()).cpu().numpy()
+            cases = []
+            for s in range(len(raw)):
+                mine = lp[fo[s]:fo[s] + fl[s]]
+                assert np.array_equal(mine.view(np.int32), alone[fo[s]:fo[s] + fl[s]].view(np.int32))   # same arithmetic in both kernels
+                ref = torch.log_softmax(torch.from_numpy(raw[s]), -1).numpy()
+                np.testing.assert_allclose(mine, ref, rtol=0, atol=4e-6)
+                cases.append((mine.copy(), toks[s]))
+            spec2 = BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank)
+            check_against_oracle(spec2, res, cases, blank, full=False)
+            # path log-probs are taken from the same values
+            for s, (mine, tk) in enumerate(cases):
+                p = c_oracle.walk_back(c_oracle.forward_trellis(mine, tk, blank), mine, tk, blank)
+                pt = res.path_token[fo[s]:fo[s] + fl[s]].numpy()
+                on = np.nonzero(pt >= 0)[0]
+                assert p is not None and on.tolist() == p["time"].tolist()
+                assert np.array_equal(res.path_logp[fo[s]:fo[s] + fl[s]].numpy()[on].view(np.int32), p["logp"].view(np.int32))
+
+
+def test_host_entry_point_matches_device(engine):
+    rng = np.random.default_rng(33)
+    cases = [(logprobs(rng, int(t), 29), rng.integers(0, 29, max(int(t) // 3, 1)).astype(np.int32))
+             for t in rng.integers(5, 400, 40)]
+    spec, a = run(engine, cases, 29, 0, align=4, want=("path",))
+    _, b = run(engine, cases, 29, 0, align=4, want=("path",), host=True)
+    for f in ("status", "n_frames", "char_start", "char_end", "char_score"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    for s in range(len(cases)):          # per-frame outputs: rows between segments are alignment padding
+        sl = slice(int(spec.frame_off[s]), int(spec.frame_off[s] + spec.frame_len[s]))
+        assert torch.equal(a.path_token[sl], b.path_token[sl]) and torch.equal(a.path_logp[sl], b.path_logp[sl])
+    check_against_oracle(spec, b, cases, 0, full=False)
+
+
+def test_timestamps_and_words_exact(engine):
+    """Device-side round(x, 3) and numpy-order word means against Python / pandas arithmetic."""
+    import pandas as pd
+    rng = np.random.default_rng(77)
+    cases, t1s, ratios, np_flags, word_off, wchar_off, wchar_idx = [], [], [], [], [0], [0], []
+    for c in range(40):
+        T = int(rng.integers(20, 500)); N = int(rng.integers(1, min(T, 200)))
+        cases.append((logprobs(rng, T, 29), rng.integers(0, 29, N).astype(np.int32)))
+        t1 = round(float(rng.random() * 1000), 3); dur = float(rng.random() * 30 + 0.1)
+        t1s.append(t1); ratios.append(dur * 1 / T); np_flags.append(c % 2)
+        # random word groups over the chars, with unalignable (-1) entries sprinkled in
+        k = 0
+        nw = 0
+        while k < N:
+            L = int(rng.integers(1, 20))
+            idx = list(range(k, min(k + L, N)))
+            k += L
+            ent = []
+            for i in idx:
+                if rng.random() < 0.15:
+                    ent.append(-1)
+                ent.append(i)
+            if rng.random() < 0.1:
+                ent = [-1] * len(ent)
+            wchar_idx += ent
+            wchar_off.append(len(wchar_idx))
+            nw += 1
+        word_off.append(word_off[-1] + nw)
+    E, fo, fl, to, tok = concat_cases(cases, 29, 4)
+    spec = BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=29, seg_t1=t1s, seg_ratio=ratios, seg_round_np=np_flags,
+                     word_off=word_off, wchar_off=wchar_off, wchar_idx=wchar_idx)
+    res = engine.align_batch(torch.from_numpy(E).cuda(), spec).cpu()
+    for s in range(len(cases)):
+        assert int(res.status[s]) == 0
+        for k in range(int(to[s]), int(to[s + 1])):
+            # odd segments emulate numpy-typed segment times: np.float64 arithmetic and rounding
+            cast = np.float64 if np_flags[s] else float
+            assert float(res.char_start_s[k]) == round(int(res.char_start[k]) * cast(ratios[s]) + cast(t1s[s]), 3)
+            assert float(res.char_end_s[k]) == round(int(res.char_end[k]) * cast(ratios[s]) + cast(t1s[s]), 3)
+            assert float(res.char_score_r[k]) == round(float(res.char_score[k]), 3)
+        for w in range(word_off[s], word_off[s + 1]):
+            ent = wchar_idx[wchar_off[w]:wchar_off[w + 1]]
+            df = pd.DataFrame({
+                "start": [float(res.char_start_s[to[s] + i]) if i >= 0 else None for i in ent],
+                "end": [float(res.char_end_s[to[s] + i]) if i >= 0 else None for i in ent],
+                "score": [float(res.char_score_r[to[s] + i]) if i >= 0 else None for i in ent]}, dtype=float)
+            ws, we, wsc = df["start"].min(), df["end"].max(), round(df["score"].mean(), 3)
+            for got, exp in ((res.word_start_s[w], ws), (res.word_end_s[w], we), (res.word_score[w], wsc)):
+                assert (np.isnan(exp) and np.isnan(float(got))) or float(got) == exp, (s, w, float(got), exp)
+
+
+def test_full_size_properties(engine):
+    """BASELINE config 2 at full size (4,096 segments of 5-30 s): size-independent properties +
+    a sampled oracle comparison."""
+    b = synth.make_batch(4096, "c2", align_frames=4, kind="planted")
+    E = torch.log_softmax(torch.from_numpy(b.emissions).cuda(), -1)
+    spec = BatchSpec(frame_off=b.frame_off, frame_len=b.frame_len, tok_off=b.tok_off, tokens=b.tokens,
+                     vocab=b.vocab, blank_id=b.blank)
+    res = engine.align_batch(E, spec).cpu()
+    assert int(res.status.sum()) == 0
+    cs, ce = res.char_start.numpy().astype(np.int64), res.char_end.numpy().astype(np.int64)
+    to = b.tok_off
+    seg_of = np.repeat(np.arange(4096), np.diff(to))
+    assert (ce > cs).all() and (cs >= 0).all()
+    assert (ce <= b.frame_len[seg_of]).all()
+    # inside a segment: token k+1 starts where token k ends (monotone, gap-free path)
+    inner = np.ones(len(cs), bool); inner[to[1:] - 1] = False
+    assert np.array_equal(cs[1:][inner[:-1]], ce[:-1][inner[:-1]])
+    assert np.array_equal(ce[to[1:] - 1], res.n_frames.numpy())
+    sc = res.char_score.numpy()
+    assert ((sc > 0) & (sc <= 1.0 + 1e-12)).all()
+    Ec = E.cpu().numpy()
+    rng = np.random.default_rng(0)
+    for s in rng.choice(4096, 48, replace=False):
+        Es = Ec[b.frame_off[s]:b.frame_off[s] + b.frame_len[s]]
+        tk = b.tokens[to[s]:to[s + 1]]
+        rc, ocs, oce, osc, ts = c_oracle.align_segment(Es, tk, b.blank)
+        assert rc == 0 and np.array_equal(ocs, cs[to[s]:to[s + 1]]) and np.array_equal(oce, ce[to[s]:to[s + 1]])
+        np.testing.assert_allclose(sc[to[s]:to[s + 1]], osc, rtol=SCORE_RTOL, atol=0)
+
+
+def test_backtrack_from_trellis_kernel(engine, golden_dp):
+    meta, arr = golden_dp
+    for m in meta[::3]:
+        n = m["name"]
+        st, ts, pt, pl = engine.backtrack_trellis(torch.from_numpy(arr[n + "_R"]), torch.from_numpy(arr[n + "_E"]),
+                                                  arr[n + "_tok"].tolist(), m["blank"])
+        assert st == (0 if m["ok"] else 1)
+        if m["ok"]:
+            on = np.nonzero(pt.numpy() >= 0)[0]
+            assert on.tolist() == arr[n + "_ptime"].tolist() and pt.numpy()[on].tolist() == arr[n + "_ptok"].tolist()
+            assert torch.exp(pl[on]).double().tolist() == arr[n + "_pscore"].tolist()

@@ -28,7 +28,7 @@ class Batch(C.Structure):
         ("n_segments", C.c_int64), ("vocab", C.c_int32), ("blank_id", C.c_int32),
         ("flags", C.c_uint32), ("reserved", C.c_uint32),
         ("frame_off", i64p), ("frame_len", i32p), ("tok_off", i64p), ("tokens", i32p),
-        ("seg_t1", f64p), ("seg_ratio", f64p),
+        ("seg_t1", f64p), ("seg_ratio", f64p), ("seg_round_np", C.POINTER(C.c_uint8)),
         ("n_words", C.c_int64), ("word_off", i64p), ("wchar_off", i64p), ("wchar_idx", i32p),
     ]
 
@@ -53,8 +53,8 @@ class Limits(C.Structure):
 SYMBOLS = (
     "wxb_abi_version", "wxb_last_error", "wxb_create", "wxb_destroy", "wxb_get_limits",
     "wxb_plan_create", "wxb_plan_destroy", "wxb_plan_launch_count", "wxb_plan_stats",
-    "wxb_plan_run", "wxb_align_device", "wxb_align_host", "wxb_log_softmax_device",
-    "wxb_backtrack_trellis_device", "wxb_round3", "wxb_pairwise_sum", "wxb_tokens_per_lane",
+    "wxb_plan_run", "wxb_plan_debug_trace", "wxb_align_device", "wxb_align_host", "wxb_log_softmax_device",
+    "wxb_backtrack_trellis_device", "wxb_round3", "wxb_round3_np", "wxb_pairwise_sum", "wxb_tokens_per_lane",
 )
 
 _LIB = None
@@ -84,6 +84,8 @@ def load(build_if_missing: bool = True):
     L.wxb_plan_launch_count.argtypes = [vp]
     L.wxb_plan_stats.argtypes = [vp, i64p, i64p, i64p]
     L.wxb_plan_run.argtypes = [vp, vp, C.POINTER(Outputs), vp, f32p]
+    L.wxb_plan_debug_trace.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int64]
+    L.wxb_plan_debug_trace.restype = C.c_int
     L.wxb_align_device.argtypes = [vp, C.POINTER(Batch), vp, C.POINTER(Outputs), vp]
     L.wxb_align_host.argtypes = [vp, C.POINTER(Batch), vp, C.POINTER(Outputs)]
     L.wxb_log_softmax_device.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp]
@@ -91,11 +93,13 @@ def load(build_if_missing: bool = True):
                                                vp, vp, vp, vp, vp]
     L.wxb_round3.argtypes = [C.c_double]
     L.wxb_round3.restype = C.c_double
+    L.wxb_round3_np.argtypes = [C.c_double]
+    L.wxb_round3_np.restype = C.c_double
     L.wxb_pairwise_sum.argtypes = [f64p, C.c_int64]
     L.wxb_pairwise_sum.restype = C.c_double
     L.wxb_tokens_per_lane.argtypes = [C.c_int32]
     for name in ("wxb_create", "wxb_get_limits", "wxb_plan_create", "wxb_plan_launch_count", "wxb_plan_stats",
-                 "wxb_plan_run", "wxb_align_device", "wxb_align_host", "wxb_log_softmax_device",
+                 "wxb_plan_run", "wxb_plan_debug_trace", "wxb_align_device", "wxb_align_host", "wxb_log_softmax_device",
                  "wxb_backtrack_trellis_device", "wxb_tokens_per_lane"):
         getattr(L, name).restype = C.c_int
     if L.wxb_abi_version() != 1:

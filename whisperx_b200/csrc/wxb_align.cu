@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -39,13 +40,13 @@ static cudaError_t launch_k(int k, const Params &p, int first, int count, size_t
 }
 
 // ------------------------------------------------------------------ small kernels
-struct ShortSeg { long long tok_base; int N; int seg; };
+struct ShortSeg { long long tok_base; long long frame_base; int N; int T; int seg; int pad; };
 
 // Segments the planner proved un-alignable (N == 0 or N > T: column N of the trellis is -inf in
 // every row, so argmax = 0 and the walk is empty — alignment.py:396-420) get the FAILED record.
 __global__ void mark_failed_kernel(const ShortSeg *list, int n, int *status, int *nframes, int *c_start,
                                    int *c_end, double *c_score, double *c_start_s, double *c_end_s,
-                                   double *c_score_r) {
+                                   double *c_score_r, int *path_tok, float *path_logp) {
     const int i = blockIdx.x;
     if (i >= n) return;
     const ShortSeg s = list[i];
@@ -56,11 +57,76 @@ __global__ void mark_failed_kernel(const ShortSeg *list, int n, int *status, int
         c_start[o] = -1; c_end[o] = -1; c_score[o] = nan;
         if (c_start_s) { c_start_s[o] = nan; c_end_s[o] = nan; c_score_r[o] = nan; }
     }
+    if (path_tok)
+        for (int f = threadIdx.x; f < s.T; f += blockDim.x) { path_tok[s.frame_base + f] = -1; path_logp[s.frame_base + f] = 0.0f; }
+}
+
+// ---- phase 3 as its own kernel: one thread per token of every segment ----
+// merge_repeats (:438-454): token k spans frames [start_k, start_{k+1}) (the last one ends at
+// t_start); its score is the mean of the path probabilities: exp(logp[start, token]) for the frame
+// that entered it and exp(logp[f, 0]) — literal column 0 (:409) — for the frames that stayed.
+// Char timestamps (:252-264): round(frame*ratio + t1, 3), round(score, 3).
+__global__ void __launch_bounds__(128) finalize_kernel(const Params p, const FinBlock *blocks) {
+    const FinBlock fb = blocks[blockIdx.x];
+    const SegDesc d = p.segs[fb.desc];
+    const int N = d.N, T = d.T, V = p.V;
+    const int status = p.status[d.seg];
+    const int t_start = p.nframes[d.seg];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool want_sec = (p.seg_t1 != nullptr) && (p.c_start_s != nullptr);
+    if (p.path_tok && fb.k0 == 0) {
+        // frames off the path: everything on failure, else [0, start_0) and [t_start, T)
+        const int first = status ? T : p.c_start[d.tok_base];
+        for (int f = threadIdx.x; f < T; f += blockDim.x)
+            if (status || f < first || f >= t_start) { p.path_tok[d.frame_base + f] = -1; p.path_logp[d.frame_base + f] = 0.0f; }
+    }
+    const int k = fb.k0 + threadIdx.x;
+    if (k >= N) return;
+    const long long o = d.tok_base + k;
+    if (status) {
+        p.c_start[o] = -1;
+        p.c_end[o] = -1;
+        p.c_score[o] = nan;
+        if (want_sec) { p.c_start_s[o] = nan; p.c_end_s[o] = nan; p.c_score_r[o] = nan; }
+        return;
+    }
+    const float *Eg = p.emis + d.emis_off;
+    const int sf = p.c_start[o];
+    const int ef = (k == N - 1) ? t_start : p.c_start[o + 1];
+    const int tk = __ldg(p.tokens + o);
+    float x = __ldg(Eg + static_cast<size_t>(sf) * V + tk);
+    if (p.is_logits) x = logp_from(x, p.rowmax[d.frame_base + sf], p.rowlse[d.frame_base + sf]);
+    double sum = static_cast<double>(expf(x));           // Python sum(): 0 + p_first + ...
+    for (int f = sf + 1; f < ef; ++f) sum += static_cast<double>(p.p0[d.frame_base + f]);
+    const double score = sum / static_cast<double>(ef - sf);
+    p.c_end[o] = ef;
+    p.c_score[o] = score;
+    if (want_sec) {
+        const double t1 = p.seg_t1[d.seg], ratio = p.seg_ratio[d.seg];
+        const double ts = __dadd_rn(__dmul_rn(static_cast<double>(sf), ratio), t1);
+        const double te = __dadd_rn(__dmul_rn(static_cast<double>(ef), ratio), t1);
+        // numpy-typed segment times make `frame*ratio + t1` a np.float64, whose round() is numpy's
+        const bool np_times = p.seg_round_np != nullptr && p.seg_round_np[d.seg] != 0;
+        p.c_start_s[o] = np_times ? round3_np(ts) : round3(ts);
+        p.c_end_s[o] = np_times ? round3_np(te) : round3(te);
+        p.c_score_r[o] = round3(score);                 // Segment.score is always a Python float
+    }
+    if (p.path_tok) {
+        p.path_tok[d.frame_base + sf] = k;
+        p.path_logp[d.frame_base + sf] = x;
+        for (int f = sf + 1; f < ef; ++f) {
+            float e0 = __ldg(Eg + static_cast<size_t>(f) * V);
+            if (p.is_logits) e0 = logp_from(e0, p.rowmax[d.frame_base + f], p.rowlse[d.frame_base + f]);
+            p.path_tok[d.frame_base + f] = k;
+            p.path_logp[d.frame_base + f] = e0;
+        }
+    }
 }
 
 // Word reduction, alignment.py:297-320: start = min, end = max over the word's aligned chars
 // (first / last aligned char: rounded times are monotone in the frame index), score =
-// round(mean(rounded char scores), 3) with pandas' zero-filled numpy pairwise sum / count.
+// round(mean(rounded char scores), 3) with pandas' zero-filled numpy pairwise sum / count; the
+// mean is a np.float64, so that round() is numpy's (rint(x*1000)/1000), not Python's.
 __global__ void word_reduce_kernel(long long W, const int *word_seg, const long long *seg_tok_base,
                                    const long long *wchar_off, const int *wchar_idx, const int *status,
                                    const double *c_start_s, const double *c_end_s, const double *c_score_r,
@@ -85,7 +151,7 @@ __global__ void word_reduce_kernel(long long W, const int *word_seg, const long 
         [&](long i) { const int idx = wchar_idx[lo + i]; return idx >= 0 ? c_score_r[base + idx] : 0.0; }, n);
     w_start[w] = c_start_s[base + first];
     w_end[w] = c_end_s[base + last];
-    w_score[w] = round3(sum / static_cast<double>(count));
+    w_score[w] = round3_np(sum / static_cast<double>(count));   // np.float64.__round__, not Python round
 }
 
 // Kernel (i) on its own — torch.log_softmax(emissions, dim=-1), alignment.py:233.
@@ -219,7 +285,9 @@ struct wxb_ctx {
     cudaStream_t main = nullptr;              // used by wxb_align_host
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
-    DevBuf bits, p0, rowmax, rowlse, nframes_scratch;
+    DevBuf bits, p0, rowmax, rowlse, nframes_scratch, trace;
+    int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
+    bool want_trace = false;                  // WXB_TRACE=1
     // wxb_align_host staging
     DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
 };
@@ -232,13 +300,17 @@ struct wxb_plan {
     int V = 0, blank = 0, TE = 32;
     uint32_t flags = 0;
     size_t smem = 0;
-    bool has_sec = false, has_words = false;
+    bool has_sec = false, has_words = false, has_round_np = false;
     std::vector<Bucket> buckets;
     int n_short = 0;
     long long bits_words = 0, trellis_floats = 0, cells = 0, alg_bytes = 0;
+    int n_fin_blocks = 0, n_desc = 0;
+    std::vector<SegDesc> host_descs;          // kept for wxb_plan_debug_trace
+    DevBuf d_fin;
+    DevBuf d_round_np;
     DevBuf d_segs, d_tokens, d_tok4, d_t1, d_ratio, d_short, d_word_seg, d_seg_tok_base, d_wchar_off, d_wchar_idx;
     ~wxb_plan() {
-        DevBuf *all[] = {&d_segs, &d_tokens, &d_tok4, &d_t1, &d_ratio, &d_short, &d_word_seg, &d_seg_tok_base, &d_wchar_off, &d_wchar_idx};
+        DevBuf *all[] = {&d_round_np, &d_fin, &d_segs, &d_tokens, &d_tok4, &d_t1, &d_ratio, &d_short, &d_word_seg, &d_seg_tok_base, &d_wchar_off, &d_wchar_idx};
         for (DevBuf *b : all) b->release();
     }
 };
@@ -270,6 +342,7 @@ static int pick_tile(int V, int *TE, size_t *smem) {
 extern "C" int wxb_abi_version(void) { return WXB_ABI_VERSION; }
 extern "C" const char *wxb_last_error(void) { return g_err.c_str(); }
 extern "C" double wxb_round3(double x) { return wxb::round3(x); }
+extern "C" double wxb_round3_np(double x) { return wxb::round3_np(x); }
 extern "C" double wxb_pairwise_sum(const double *a, int64_t n) {
     return wxb::pairwise_sum([&](long i) { return a[i]; }, static_cast<long>(n));
 }
@@ -289,6 +362,8 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     wxb_ctx *c = new (std::nothrow) wxb_ctx();
     if (!c) return fail(WXB_ENOMEM, "wxb_create: out of host memory");
     c->device = device;
+    if (const char *e = getenv("WXB_SIDE_STREAMS")) c->side_streams = std::max(1, std::min(NSIDE, atoi(e)));
+    if (const char *e = getenv("WXB_TRACE")) c->want_trace = atoi(e) != 0;
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
     for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
@@ -307,7 +382,7 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
 extern "C" void wxb_destroy(wxb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf *bufs[] = {&c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->nframes_scratch, &c->h_emis, &c->h_path_tok};
+    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->nframes_scratch, &c->h_emis, &c->h_path_tok};
     for (DevBuf *b : bufs) b->release();
     for (auto &b : c->h_i32) b.release();
     for (auto &b : c->h_f64) b.release();
@@ -399,7 +474,7 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
         trellis_off += static_cast<long long>(T + 1) * (N + 1);
         const int K = tokens_per_lane(N);
         if (N == 0 || (N > T && (!no_shortcut || K < 0))) {
-            shorts.push_back({to[s], N, static_cast<int>(s)});
+            shorts.push_back({to[s], fo[s], N, T, static_cast<int>(s), 0});
             continue;
         }
         if (K < 0)
@@ -431,19 +506,28 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
         pl->buckets.back().cost += static_cast<long long>(descs[i].T) * descs[i].K;
     }
     pl->bits_words = bits;
+    std::vector<FinBlock> fin;
+    for (size_t i = 0; i < descs.size(); ++i)
+        for (int k0 = 0; k0 < descs[i].N; k0 += 128) fin.push_back({static_cast<int>(i), k0});
+    pl->n_fin_blocks = static_cast<int>(fin.size());
+    pl->n_desc = static_cast<int>(descs.size());
+    pl->host_descs = descs;
     std::stable_sort(pl->buckets.begin(), pl->buckets.end(), [](const Bucket &a, const Bucket &b) { return a.cost > b.cost; });
 
     // ---- upload ----
     std::vector<int> tok4(static_cast<size_t>(std::max<int64_t>(pl->sum_N, 1)));
     for (int64_t i = 0; i < pl->sum_N; ++i) tok4[i] = bt->tokens[i] * 4;
     CUDA_TRY(upload(pl->d_segs, descs.data(), descs.size()));
+    CUDA_TRY(upload(pl->d_fin, fin.data(), fin.size()));
     CUDA_TRY(upload(pl->d_tokens, bt->tokens, static_cast<size_t>(pl->sum_N)));
     CUDA_TRY(upload(pl->d_tok4, tok4.data(), static_cast<size_t>(pl->sum_N)));
     CUDA_TRY(upload(pl->d_short, shorts.data(), shorts.size()));
     if (pl->has_sec) {
         CUDA_TRY(upload(pl->d_t1, bt->seg_t1, static_cast<size_t>(S)));
         CUDA_TRY(upload(pl->d_ratio, bt->seg_ratio, static_cast<size_t>(S)));
+        if (bt->seg_round_np) CUDA_TRY(upload(pl->d_round_np, bt->seg_round_np, static_cast<size_t>(S)));
     }
+    pl->has_round_np = pl->has_sec && bt->seg_round_np != nullptr;
     if (pl->has_words) {
         const int64_t W = pl->W;
         if (bt->word_off[0] != 0 || bt->word_off[S] != W) return fail(WXB_EINVAL, "wxb_plan_create: word_off must run from 0 to n_words");
@@ -476,7 +560,7 @@ extern "C" void wxb_plan_destroy(wxb_plan *plan) {
 
 extern "C" int wxb_plan_launch_count(const wxb_plan *plan) {
     if (!plan) return 0;
-    return static_cast<int>(plan->buckets.size()) + (plan->n_short > 0 ? 1 : 0) + (plan->has_words ? 1 : 0);
+    return static_cast<int>(plan->buckets.size()) + (plan->n_fin_blocks > 0 ? 1 : 0) + (plan->n_short > 0 ? 1 : 0) + (plan->has_words ? 1 : 0);
 }
 
 extern "C" int wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg_bytes, int64_t *n_shortcut) {
@@ -536,9 +620,14 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     if (want_sec) {
         P.c_start_s = o->char_start_s; P.c_end_s = o->char_end_s; P.c_score_r = o->char_score_r;
         P.seg_t1 = pl->d_t1.as<double>(); P.seg_ratio = pl->d_ratio.as<double>();
+        P.seg_round_np = pl->has_round_np ? pl->d_round_np.as<unsigned char>() : nullptr;
     }
     P.path_tok = o->path_token; P.path_logp = o->path_logp;
     P.final_col = o->final_col; P.trellis = o->trellis; P.logprobs = o->logprobs;
+    if (c->want_trace) {
+        CUDA_TRY(c->trace.ensure(static_cast<size_t>(std::max(pl->n_desc, 1)) * 32));
+        P.trace = c->trace.as<unsigned long long>();
+    }
 
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t0, st));
     const int nb = static_cast<int>(pl->buckets.size());
@@ -547,7 +636,7 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
         CUDA_TRY(launch_k(b.K, P, b.first, b.count, pl->smem, st, debug));
     } else if (nb > 1) {
         // buckets are independent: fork onto side streams so that every SM sees a mix of K classes
-        const int used = std::min(nb, NSIDE);
+        const int used = std::min(nb, c->side_streams);
         CUDA_TRY(cudaEventRecord(c->ev_fork, st));
         for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
         for (int i = 0; i < nb; ++i) {
@@ -560,10 +649,14 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
         }
     }
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t1, st));
+    if (pl->n_fin_blocks > 0) {
+        finalize_kernel<<<pl->n_fin_blocks, 128, 0, st>>>(P, pl->d_fin.as<FinBlock>());
+        CUDA_TRY(cudaGetLastError());
+    }
     if (pl->n_short > 0) {
         mark_failed_kernel<<<pl->n_short, 64, 0, st>>>(pl->d_short.as<ShortSeg>(), pl->n_short, o->status, nframes,
                                                         o->char_start, o->char_end, o->char_score,
-                                                        want_sec ? o->char_start_s : nullptr, o->char_end_s, o->char_score_r);
+                                                        want_sec ? o->char_start_s : nullptr, o->char_end_s, o->char_score_r, o->path_token, o->path_logp);
         CUDA_TRY(cudaGetLastError());
     }
     if (want_words) {
@@ -651,6 +744,26 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
 #undef WXB_D2H
     CUDA_TRY(cudaStreamSynchronize(st));
     return WXB_OK;
+}
+
+// Debug aid (not part of the alignment path): per-CTA timeline of the last wxb_plan_run when the
+// ctx was created with WXB_TRACE=1.  rows[i] = {t_begin_ns, t_forward_done_ns, t_end_ns, smid, T, N, K, seg}.
+extern "C" int wxb_plan_debug_trace(wxb_plan *pl, uint64_t *rows, int64_t cap_rows) {
+    if (!pl || !rows) return fail(WXB_EINVAL, "wxb_plan_debug_trace: NULL argument");
+    wxb_ctx *c = pl->ctx;
+    if (!c->want_trace || !c->trace.p) return fail(WXB_EINVAL, "wxb_plan_debug_trace: create the ctx with WXB_TRACE=1 and run the plan first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const int n = static_cast<int>(std::min<int64_t>(pl->n_desc, cap_rows));
+    std::vector<unsigned long long> raw(static_cast<size_t>(std::max(n, 1)) * 4);
+    CUDA_TRY(cudaMemcpy(raw.data(), c->trace.p, static_cast<size_t>(n) * 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const SegDesc &d = pl->host_descs[i];
+        uint64_t *r = rows + 8ll * i;
+        r[0] = raw[4 * i + 0]; r[1] = raw[4 * i + 1]; r[2] = raw[4 * i + 2]; r[3] = raw[4 * i + 3];
+        r[4] = d.T; r[5] = d.N; r[6] = d.K; r[7] = d.seg;
+    }
+    return n;
 }
 
 // ------------------------------------------------------------------ ABI: stand-alone kernels

@@ -1,6 +1,7 @@
 // Exact host/device helpers shared by the kernels and the C ABI (single source => same bits).
 //
 //   round3()        Python round(x, 3)  — reference use: whisperx/alignment.py:262-264, 308
+//   round3_np()     np.float64.__round__(3)      — alignment.py:308 (and :262-264 for numpy-typed times)
 //   pairwise_sum()  numpy add.reduce order behind pandas .mean() — alignment.py:308
 //   row_log_softmax torch.log_softmax(dim=-1) formula — alignment.py:233
 //
@@ -44,6 +45,13 @@ WXB_HD double round3(double x) {
     const double m = up ? n + 1.0 : n;
     const double r = m / 1000.0;
     return x < 0.0 ? -r : r;
+}
+
+// round(x, 3) when x is a numpy float64 scalar (np.float64.__round__ == np.round): scale, rint
+// (half to even on the *scaled binary* value), unscale.  Differs from round3() in ~2% of word
+// means; the reference's word score is round(Series.mean(), 3) on a np.float64 (alignment.py:308).
+WXB_HD double round3_np(double x) {
+    return rint(x * 1000.0) / 1000.0;
 }
 
 // numpy pairwise_sum_DOUBLE (numpy/_core/src/umath/loops_utils.h.src) over a[idx(i)], i in [0,n).

@@ -4,8 +4,8 @@
 //   log_softmax            whisperx/alignment.py:233      (fused into the tile staging, optional)
 //   get_trellis            whisperx/alignment.py:359-379  (phase 1: recurrence, token axis in registers)
 //   backtrack              whisperx/alignment.py:387-421  (phase 2: walk over packed choice bits)
-//   merge_repeats          whisperx/alignment.py:438-454  (phase 3: per-token start/end/mean prob)
-//   char timestamps        whisperx/alignment.py:252-264  (phase 3: exact decimal rounding)
+//   merge_repeats          whisperx/alignment.py:438-454  (finalize_kernel: per-token start/end/mean prob)
+//   char timestamps        whisperx/alignment.py:252-264  (finalize_kernel: exact decimal rounding)
 //
 // Data movement: the segment's emission rows [T,V] are streamed HBM -> shared memory exactly once,
 // TE frames per tile, double buffered, with one cp.async.bulk (TMA bulk copy, mbarrier completion)
@@ -46,13 +46,20 @@ struct Params {
     int *c_start, *c_end;
     double *c_score, *c_start_s, *c_end_s, *c_score_r;
     const double *seg_t1, *seg_ratio;
+    const unsigned char *seg_round_np;   // [S] or null: 1 = numpy rounding for this segment's timestamps
     int *path_tok;
     float *path_logp, *final_col, *trellis, *logprobs;
+    unsigned long long *trace;   // debug: [4 * n_desc] {t_begin, t_forward_done, t_end, smid} per CTA, or null
 };
 
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int SM_TAIL_BYTES = 144 + 256 + 16;   // col0[36] floats + xd[32] doubles + 2 mbarriers
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -111,6 +118,12 @@ __global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg
     const int lane = threadIdx.x;
     const SegDesc d = p.segs[seg_first + blockIdx.x];
     const int T = d.T, N = d.N, V = p.V, TE = p.TE;
+    if (p.trace && lane == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        p.trace[4ll * (seg_first + blockIdx.x) + 0] = global_ns();
+        p.trace[4ll * (seg_first + blockIdx.x) + 3] = smid;
+    }
     const uint32_t tile_bytes = static_cast<uint32_t>(TE * V) * 4u;
     float *col0_s = reinterpret_cast<float *>(sm + 2 * tile_bytes);
     double *xd_s = reinterpret_cast<double *>(sm + 2 * tile_bytes + 144);
@@ -245,15 +258,28 @@ __global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg
             const float c0 = col0_s[tt];
             float left = __shfl_up_sync(FULL, src, 1);
             if (lane == 0) left = c0;
+            // chg first (it reads the *old* left neighbours), then stay / sign-difference as packed
+            // f32x2 adds (FADD2 on sm_100: one issue slot for two cells; IEEE round-to-nearest per lane)
+            float chg[K];
 #pragma unroll
             for (int i = K - 1; i >= 0; --i) {
                 const float e = lds_f32(rowaddr + tokoff[i]);
-                const float prev = (i == 0) ? left : R[i - 1];
-                const float chg = prev + e;                 // trellis[t, j-1] + emission[t, tokens[j-1]]
-                const float stay = R[i] + eb;               // trellis[t, j]   + emission[t, blank]
-                R[i] = fmax_nan(stay, chg);
-                const float dd = stay - chg;                // sign bit set  <=>  chg > stay (strict)
-                acc[i] = __funnelshift_l(__float_as_uint(dd), acc[i], 1);
+                chg[i] = ((i == 0) ? left : R[i - 1]) + e;    // trellis[t, j-1] + emission[t, tokens[j-1]]
+            }
+#pragma unroll
+            for (int i = 0; i + 1 < K; i += 2) {
+                const float2 st = __fadd2_rn(make_float2(R[i], R[i + 1]), make_float2(eb, eb));   // trellis[t, j] + emission[t, blank]
+                const float2 dd = __fadd2_rn(st, make_float2(-chg[i], -chg[i + 1]));             // sign set <=> chg > stay (strict)
+                R[i] = fmax_nan(st.x, chg[i]);
+                R[i + 1] = fmax_nan(st.y, chg[i + 1]);
+                acc[i] = __funnelshift_l(__float_as_uint(dd.x), acc[i], 1);
+                acc[i + 1] = __funnelshift_l(__float_as_uint(dd.y), acc[i + 1], 1);
+            }
+            if (K & 1) {
+                const float stay = R[K - 1] + eb;
+                const float dd = stay - chg[K - 1];
+                R[K - 1] = fmax_nan(stay, chg[K - 1]);
+                acc[K - 1] = __funnelshift_l(__float_as_uint(dd), acc[K - 1], 1);
             }
             rowaddr += rowstep;
             ++t;
@@ -300,8 +326,14 @@ __global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg
     }
     __threadfence_block();
     __syncwarp();
+    if (p.trace && lane == 0) p.trace[4ll * (seg_first + blockIdx.x) + 1] = global_ns();
 
-    // ---- phase 2: backtrack (:395-421) over the choice bits; uniform across the warp ----
+    // ---- phase 2: backtrack (:395-421) over the choice bits; control flow is warp-uniform ----
+    // The walk needs one choice word per visited (column, 32-frame word) pair: ~N + T/32
+    // *dependent* loads if done naively (measured: 30% of all warp time).  Instead the warp
+    // fetches a window of 32 columns x 4 words (128 frames) with 4 independent loads per lane
+    // and walks inside it on register shuffles; a new window is fetched only when the path leaves
+    // the block: about max(N/32, T/128) dependent round trips per segment.
     const int t_start = __shfl_sync(FULL, bestt, laneN);
     int status = 0;
     int *cstart = p.c_start + d.tok_base;
@@ -310,86 +342,50 @@ __global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg
     } else {
         int j = N;
         int s = t_start - 1;                         // frame of the current point
-        while (true) {
-            int ln, slot;
-            owner_of<K>(j - 1, r, ln, slot);
-            const uint32_t word = __ldcg(p.bits + d.bits_off + (static_cast<long long>(s >> 5) * K + slot) * 32 + ln);
-            // bit (31 - s%32) is frame s; shift so that bit 0 = frame s, bit q = frame s-q
-            const int q0 = s & 31;
-            uint32_t m = word >> (31 - q0);
-            // m now holds frames s, s-1, ... s-q0 in bits 0..q0 (higher bits are zero)
-            if (m == 0u) {
-                s = (s & ~31) - 1;                   // stayed through the rest of this word
-                if (s < 0) { status = 1; break; }
-            } else {
-                const int q = __ffs(m) - 1;
-                const int sc = s - q;                // frame at which token j-1 was entered
-                if (lane == 0) cstart[j - 1] = sc;
-                --j;
-                if (j == 0) break;
-                s = sc - 1;
-                if (s < 0) { status = 1; break; }
+        bool done = false;
+        while (!done) {
+            const int j0 = j;                        // window columns j0, j0-1, ..., j0-31
+            const int w0 = s >> 5;                   // window words   w0, w0-1, w0-2, w0-3
+            uint32_t wA = 0u, wB = 0u, wC = 0u, wD = 0u;
+            const int c = j0 - lane;
+            if (c >= 1) {
+                int ln, slot;
+                owner_of<K>(c - 1, r, ln, slot);
+                const uint32_t *bp = p.bits + d.bits_off + (static_cast<long long>(w0) * K + slot) * 32 + ln;
+                wA = __ldcg(bp);
+                if (w0 >= 1) wB = __ldcg(bp - 1 * K * 32);
+                if (w0 >= 2) wC = __ldcg(bp - 2 * K * 32);
+                if (w0 >= 3) wD = __ldcg(bp - 3 * K * 32);
+            }
+            while (true) {
+                const int dw = w0 - (s >> 5);        // 0..3 inside the window
+                const uint32_t mine = (dw == 0) ? wA : (dw == 1) ? wB : (dw == 2) ? wC : wD;
+                const uint32_t word = __shfl_sync(FULL, mine, j0 - j);
+                // bit (31 - f%32) is frame f; shift so that bit 0 = frame s, bit q = frame s-q
+                const uint32_t m = word >> (31 - (s & 31));
+                if (m == 0u) {
+                    s = (s & ~31) - 1;               // stayed through the rest of this word
+                    if (s < 0) { status = 1; done = true; break; }
+                } else {
+                    const int sc = s - (__ffs(m) - 1);   // frame at which token j-1 was entered
+                    if (lane == 0) cstart[j - 1] = sc;
+                    --j;
+                    if (j == 0) { done = true; break; }
+                    s = sc - 1;
+                    if (s < 0) { status = 1; done = true; break; }
+                }
+                if (j < j0 - 31 || (s >> 5) < w0 - 3) break;     // left the window: fetch the next one
             }
         }
     }
     if (lane == 0) {
         p.status[d.seg] = status;
         p.nframes[d.seg] = status ? 0 : t_start;
+        if (p.trace) p.trace[4ll * (seg_first + blockIdx.x) + 2] = global_ns();
     }
-    __threadfence_block();
-    __syncwarp();
-
-    // ---- phase 3: merge_repeats (:438-454) + char timestamps (:252-264), one token per lane ----
-    const bool want_sec = (p.seg_t1 != nullptr) && (p.c_start_s != nullptr);
-    const double t1 = want_sec ? p.seg_t1[d.seg] : 0.0;
-    const double ratio = want_sec ? p.seg_ratio[d.seg] : 0.0;
-    if (p.path_tok) {
-        for (int f = lane; f < T; f += 32) {
-            p.path_tok[d.frame_base + f] = -1;
-            p.path_logp[d.frame_base + f] = 0.0f;
-        }
-        __threadfence_block();
-        __syncwarp();
-    }
-    for (int k = lane; k < N; k += 32) {
-        const long long o = d.tok_base + k;
-        if (status) {
-            p.c_start[o] = -1;
-            p.c_end[o] = -1;
-            p.c_score[o] = __longlong_as_double(0x7ff8000000000000LL);
-            if (want_sec) {
-                p.c_start_s[o] = p.c_end_s[o] = p.c_score_r[o] = __longlong_as_double(0x7ff8000000000000LL);
-            }
-            continue;
-        }
-        const int sf = __ldcg(cstart + k);
-        const int ef = (k == N - 1) ? t_start : __ldcg(cstart + k + 1);
-        const int tk = __ldg(p.tokens + o);
-        // first frame of the run: the "changed" point, prob = exp(logp[sf, token])   (:409)
-        float x = __ldg(Eg + static_cast<size_t>(sf) * V + tk);
-        if (p.is_logits) x = logp_from(x, p.rowmax[d.frame_base + sf], p.rowlse[d.frame_base + sf]);
-        double sum = static_cast<double>(expf(x));
-        // remaining frames of the run: "stayed" points, prob = exp(logp[f, 0]) — literal column 0
-        for (int f = sf + 1; f < ef; ++f) sum += static_cast<double>(__ldcg(p.p0 + d.frame_base + f));
-        const double score = sum / static_cast<double>(ef - sf);
-        p.c_end[o] = ef;
-        p.c_score[o] = score;
-        if (want_sec) {
-            p.c_start_s[o] = round3(__dadd_rn(__dmul_rn(static_cast<double>(sf), ratio), t1));
-            p.c_end_s[o] = round3(__dadd_rn(__dmul_rn(static_cast<double>(ef), ratio), t1));
-            p.c_score_r[o] = round3(score);
-        }
-        if (p.path_tok) {
-            p.path_tok[d.frame_base + sf] = k;
-            p.path_logp[d.frame_base + sf] = x;
-            for (int f = sf + 1; f < ef; ++f) {
-                float e0 = __ldg(Eg + static_cast<size_t>(f) * V);
-                if (p.is_logits) e0 = logp_from(e0, p.rowmax[d.frame_base + f], p.rowlse[d.frame_base + f]);
-                p.path_tok[d.frame_base + f] = k;
-                p.path_logp[d.frame_base + f] = e0;
-            }
-        }
-    }
+    // phase 3 (merge_repeats, scores, timestamps) runs token-parallel in finalize_kernel
 }
+
+struct FinBlock { int desc; int k0; };   // finalize_kernel work item (see wxb_align.cu)
 
 }  // namespace wxb

@@ -36,6 +36,7 @@ class BatchSpec:
     no_shortcut: bool = False
     seg_t1: Optional[np.ndarray] = None      # float64 [S]
     seg_ratio: Optional[np.ndarray] = None   # float64 [S]
+    seg_round_np: Optional[np.ndarray] = None  # uint8 [S]: numpy-typed segment times (numpy rounding)
     frame_len: Optional[np.ndarray] = None   # int32 [S]; None = contiguous segments
     word_off: Optional[np.ndarray] = None    # int64 [S+1]
     wchar_off: Optional[np.ndarray] = None   # int64 [W+1]
@@ -50,6 +51,8 @@ class BatchSpec:
         if self.seg_t1 is not None:
             self.seg_t1 = _np(self.seg_t1, np.float64)
             self.seg_ratio = _np(self.seg_ratio, np.float64)
+            if self.seg_round_np is not None:
+                self.seg_round_np = _np(self.seg_round_np, np.uint8)
         if self.word_off is not None:
             self.word_off = _np(self.word_off, np.int64)
             self.wchar_off = _np(self.wchar_off, np.int64)
@@ -92,6 +95,7 @@ class BatchSpec:
         b.tokens = _ptr(self.tokens, C.c_int32)
         b.seg_t1 = _ptr(self.seg_t1, C.c_double)
         b.seg_ratio = _ptr(self.seg_ratio, C.c_double)
+        b.seg_round_np = _ptr(self.seg_round_np, C.c_uint8)
         b.n_words = self.n_words
         b.word_off = _ptr(self.word_off, C.c_int64)
         b.wchar_off = _ptr(self.wchar_off, C.c_int64)
