@@ -29,3 +29,63 @@ def concat_cases(cases, V, align=1):
         toks = [np.zeros(0, np.int32)]
     return (np.concatenate(em), np.array(fo, np.int64), np.array(fl, np.int32), np.array(to, np.int64),
             np.concatenate(toks))
+
+
+def regex_spans(text):
+    """The sentence splitter the golden align() fixtures were generated with (scripts/make_golden.py)."""
+    import re
+    spans, start = [], 0
+    for m in re.finditer(r"[.!?]+(?=\s+\S)", text):
+        spans.append((start, m.end()))
+        nxt = re.compile(r"\S").search(text, m.end())
+        start = nxt.start() if nxt else len(text)
+    spans.append((start, len(text)))
+    out = []
+    for a, b in spans:
+        while a < b and text[a].isspace():
+            a += 1
+        out.append((a, b))
+    return out
+
+
+class ScriptedModel(torch.nn.Module):
+    """Returns prepared emissions, one tensor per call, in call order (torchaudio-style signature)."""
+
+    def __init__(self, outputs, device="cpu"):
+        super().__init__()
+        self.outputs = [torch.as_tensor(o).to(device) for o in outputs]
+        self.calls = 0
+
+    def forward(self, waveform, lengths=None):
+        x = self.outputs[self.calls]
+        self.calls += 1
+        return x.unsqueeze(0), None
+
+
+LABELS = ('-', '|', 'E', 'T', 'A', 'O', 'N', 'I', 'H', 'S', 'R', 'D', 'L', 'U', 'M', 'W', 'C', 'F', 'G', 'Y',
+          'P', 'B', 'V', 'K', "'", 'X', 'J', 'Q', 'Z')     # torchaudio WAV2VEC2_ASR_BASE_960H labels
+DICTIONARY = {c.lower(): i for i, c in enumerate(LABELS)}
+
+
+def same_records(got, exp, score_tol=0.0):
+    """Compare align() records: text / timestamps exactly, scores within score_tol.  Returns a
+    description of the first difference or None."""
+    if len(got) != len(exp):
+        return f"{len(got)} records, expected {len(exp)}"
+    for i, (g, e) in enumerate(zip(got, exp)):
+        if set(g) != set(e):
+            return f"record {i}: keys {sorted(g)} != {sorted(e)}"
+        for k in e:
+            if k in ("words", "chars"):
+                d = same_records(g[k], e[k], score_tol)
+                if d:
+                    return f"record {i}.{k}: {d}"
+            elif k == "score":
+                if abs(float(g[k]) - float(e[k])) > score_tol:
+                    return f"record {i}: score {g[k]} != {e[k]}"
+            elif isinstance(e[k], float) or isinstance(g[k], float):
+                if float(g[k]) != float(e[k]):
+                    return f"record {i}: {k} {g[k]!r} != {e[k]!r}"
+            elif g[k] != e[k]:
+                return f"record {i}: {k} {g[k]!r} != {e[k]!r}"
+    return None

@@ -1,0 +1,118 @@
+"""CPU: the host side of align() (text preparation, word groups, record assembly, NaN interpolation)
+against the reference's own outputs in tests/golden/align_cases.* (scripts/make_golden.py).
+
+The per-character values come from the oracle here (torch port: bit-identical to the reference),
+the exact rounding / numpy-order mean from the library's host helpers; the GPU tests
+(test_align_gpu.py) run the same scenarios through the kernels."""
+import copy
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port
+from tests.helpers import DICTIONARY, regex_spans, same_records
+from whisperx_b200 import _native, assemble
+
+
+@pytest.fixture(autouse=True)
+def _splitter():
+    assemble.set_sentence_splitter(regex_spans)
+    yield
+    assemble.set_sentence_splitter(None)
+
+
+def _host_align(meta, emissions, lib):
+    """align() with the DP done by the oracle and everything else by the product's host code."""
+    lang = meta["lang"]
+    transcript = copy.deepcopy(meta["segments"])
+    assemble.prepare_transcript(transcript, DICTIONARY, lang)
+    max_dur = meta["audio_samples"] / 16000
+    out, k = [], 0
+    for seg in transcript:
+        plain = {"start": seg["start"], "end": seg["end"], "text": seg["text"], "words": []}
+        if meta["return_char_alignments"]:
+            plain["chars"] = []
+        if not seg["clean_char"] or seg["start"] >= max_dur:
+            out.append(plain)
+            continue
+        E = torch.from_numpy(emissions[k]); k += 1
+        tokens = [DICTIONARY[c] for c in seg["clean_char"]]
+        chars, R = ref_port.align_tokens(E, tokens, 0, "".join(seg["clean_char"]))
+        if chars is None:
+            out.append(plain)
+            continue
+        ratio = (seg["end"] - seg["start"]) * 1 / E.shape[0]
+        cs = [lib.wxb_round3(c.start * ratio + seg["start"]) for c in chars]
+        ce = [lib.wxb_round3(c.end * ratio + seg["start"]) for c in chars]
+        sc = [lib.wxb_round3(c.score) for c in chars]
+        lay = assemble.layout_segment(seg["text"], seg["clean_cdx"], seg["sentence_spans"], lang)
+        ws, we, wsc = [], [], []
+        for g in range(lay.n_groups):
+            idx = lay.group_idx[lay.group_off[g]:lay.group_off[g + 1]]
+            al = [i for i in idx if i >= 0]
+            if not al:
+                ws.append(math.nan); we.append(math.nan); wsc.append(math.nan)
+                continue
+            z = np.array([sc[i] if i >= 0 else 0.0 for i in idx], np.float64)
+            ws.append(cs[al[0]]); we.append(ce[al[-1]])
+            wsc.append(lib.wxb_round3_np(lib.wxb_pairwise_sum(z.ctypes.data_as(C.POINTER(C.c_double)), len(z)) / len(al)))
+        out += assemble.assemble_segment(seg["text"], seg["clean_cdx"], lay, seg["sentence_spans"], lang, cs, ce, sc,
+                                         ws, we, wsc, meta["interpolate_method"], meta["return_char_alignments"])
+    return transcript, out
+
+
+def test_prepare_and_assemble_match_reference(golden_align):
+    meta, arr = golden_align
+    lib = _native.load()
+    for name, m in meta.items():
+        em = [arr[f"{name}_E{i}"] for i in range(m["n_emissions"])]
+        transcript, segs = _host_align(m, em, lib)
+        for t, exp in zip(transcript, m["mutated_inputs"]):
+            assert t["clean_char"] == exp["clean_char"] and t["clean_cdx"] == exp["clean_cdx"], name
+            assert t["clean_wdx"] == exp["clean_wdx"], name
+            assert [list(s) for s in t["sentence_spans"]] == exp["sentence_spans"], name
+        diff = same_records(segs, m["result"]["segments"])
+        assert diff is None, (name, diff)
+        words = [w for s in segs for w in s["words"]]
+        assert same_records(words, m["result"]["word_segments"]) is None, name
+
+
+def test_interpolate_nans_matches_pandas():
+    import pandas as pd
+    rng = np.random.default_rng(11)
+    for method in ("nearest", "linear"):
+        for _ in range(400):
+            n = int(rng.integers(1, 12))
+            v = np.round(rng.random(n) * 30, 3)
+            v[rng.random(n) < 0.45] = np.nan
+            s = pd.Series(v)
+            exp = (s.interpolate(method=method).ffill().bfill() if s.notnull().sum() > 1 else s.ffill().bfill()).tolist()
+            got = assemble.interpolate_nans(v.tolist(), method)
+            assert len(got) == len(exp)
+            for a, b in zip(got, exp):
+                assert (a != a and b != b) or a == b, (method, v.tolist(), got, exp)
+
+
+def test_layout_word_groups():
+    text = " ab c.  d"
+    lay = assemble.layout_segment(text, [1, 2, 3, 4, 8], [(1, 6), (8, 9)], "en")
+    assert lay.word_index == [0, 0, 0, 1, 1, 1, 2, 3, 3]
+    assert lay.windows == [(1, 6), (8, 8)]
+    # window 1 = "ab c. " (inclusive end): words "ab", " c." ; the lone space that is word 2 is dropped
+    assert [w for w, _ in lay.sentence_words[0]] == ["ab", "c."]
+    assert [w for w, _ in lay.sentence_words[1]] == ["d"]
+    groups = [lay.group_idx[lay.group_off[g]:lay.group_off[g + 1]] for g in range(lay.n_groups)]
+    assert groups == [[0, 1], [3, -1], [4]]       # the space before "c" (clean index 2) is not part of the word rows
+    ja = assemble.layout_segment("ab c", [0, 1, 3], [(0, 4)], "ja")
+    assert [w for w, _ in ja.sentence_words[0]] == ["a", "b", "c"]
+
+
+def test_fallback_splitter():
+    assemble.set_sentence_splitter(assemble._fallback_spans)
+    assert assemble.sentence_spans("Hello world. It costs 20! ok") == [(0, 12), (13, 25), (26, 28)]
+    assert assemble.sentence_spans("Dr. Smith is here. Yes") == [(0, 18), (19, 22)]
+    assert assemble.sentence_spans(" lead and trail ") == [(1, 15)]
+    assert assemble.blank_id_of({"a": 1, "<pad>": 7, "b": 2}) == 7 and assemble.blank_id_of({"a": 3}) == 0

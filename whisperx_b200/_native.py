@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwxb_align.so")
+LIB_PATH = os.environ.get("WXB_LIB") or os.path.join(_HERE, "libwxb_align.so")
 
 WXB_OK = 0
 SEG_OK = 0

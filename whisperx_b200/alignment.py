@@ -1,0 +1,409 @@
+"""Drop-in for the reference's alignment stage: `load_align_model()` and `align()` with the
+reference's signatures and result dict (whisperx/alignment.py:64-97, :100-354), plus the
+functional helpers `get_trellis` / `backtrack` / `merge_repeats` / `merge_words` (:359-470).
+
+What changes is where the work happens.  The reference walks the segments one by one, copies
+every emission matrix to the host and runs the trellis, the backtrack and the pandas tables in
+Python.  Here the wav2vec2 forward (PyTorch, unchanged) leaves its logits on the GPU, all
+segments of the call are concatenated into one [sum_T, V] batch, and one pass of the sm_100a
+kernels behind the C ABI (include/wxb_align.h) does log-softmax, trellis, backtrack, repeat
+merging, timestamp rounding and the per-word reduction for every segment at once.  Only the
+per-character / per-word result arrays come back to the host, where `assemble.py` builds the
+records.  There is no CPU fallback: `device` must be a CUDA device.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import assemble
+from .assemble import LANGUAGES_WITHOUT_SPACES, PUNKT_ABBREVIATIONS, set_sentence_splitter  # noqa: F401
+from .engine import BatchSpec, _alloc_outputs, get_engine
+
+SAMPLE_RATE = 16000                       # whisperx/audio.py:13
+
+DEFAULT_ALIGN_MODELS_TORCH = {            # alignment.py:24-30
+    "en": "WAV2VEC2_ASR_BASE_960H",
+    "fr": "VOXPOPULI_ASR_BASE_10K_FR",
+    "de": "VOXPOPULI_ASR_BASE_10K_DE",
+    "es": "VOXPOPULI_ASR_BASE_10K_ES",
+    "it": "VOXPOPULI_ASR_BASE_10K_IT",
+}
+_XLSR = "jonatasgrosman/wav2vec2-large-xlsr-53-"
+DEFAULT_ALIGN_MODELS_HF = {               # alignment.py:32-61
+    **{code: _XLSR + name for code, name in (
+        ("ja", "japanese"), ("zh", "chinese-zh-cn"), ("nl", "dutch"), ("pt", "portuguese"), ("ar", "arabic"),
+        ("ru", "russian"), ("pl", "polish"), ("hu", "hungarian"), ("fi", "finnish"), ("fa", "persian"),
+        ("el", "greek"))},
+    "uk": "Yehor/wav2vec2-xls-r-300m-uk-with-small-lm",
+    "cs": "comodoro/wav2vec2-xls-r-300m-cs-250",
+    "tr": "mpoyraz/wav2vec2-xls-r-300m-cv7-turkish",
+    "da": "saattrupdan/wav2vec2-xls-r-300m-ftspeech",
+    "he": "imvladikon/wav2vec2-xls-r-300m-hebrew",
+    "vi": "nguyenvulebinh/wav2vec2-base-vi",
+    "ko": "kresnik/wav2vec2-large-xlsr-korean",
+    "ur": "kingabzpro/wav2vec2-large-xls-r-300m-Urdu",
+    "te": "anuragshas/wav2vec2-large-xlsr-53-telugu",
+    "hi": "theainerd/Wav2Vec2-large-xlsr-hindi",
+    "ca": "softcatala/wav2vec2-large-xlsr-catala",
+    "ml": "gvs/wav2vec2-large-xlsr-malayalam",
+    "no": "NbAiLab/nb-wav2vec2-1b-bokmaal",
+    "nn": "NbAiLab/nb-wav2vec2-300m-nynorsk",
+    "sk": "comodoro/wav2vec2-xls-r-300m-sk-cv8",
+    "sl": "anton-l/wav2vec2-large-xlsr-53-slovenian",
+    "hr": "classla/wav2vec2-xls-r-parlaspeech-hr",
+}
+
+# How emissions reach the kernels:
+#   "fused"  raw logits go in and log_softmax(dim=-1) happens while a tile is staged (default)
+#   "torch"  torch.log_softmax on the device first (the op the reference calls at alignment.py:233),
+#            then the kernels take log-probs
+#   "logprobs" the model's output already is log-probabilities; nothing is applied
+EMISSION_MODE = os.environ.get("WXB_EMISSION_MODE", "fused")
+# >1: segments with the same number of samples share one wav2vec2 forward;
+# 1 keeps the reference's batch-1 forwards (alignment.py:215 has this as a TODO).
+EMISSION_BATCH = int(os.environ.get("WXB_EMISSION_BATCH", "1"))
+# Introspection for the parity tests: when True, align() keeps the last batch it ran (spec, device
+# results and, in fused mode, the log-probs the kernels computed) in LAST_BATCH.
+KEEP_LAST_BATCH = False
+LAST_BATCH: dict = {}
+
+
+def load_audio(file: str, sr: int = SAMPLE_RATE) -> np.ndarray:
+    """Decode `file` to mono float32 at `sr` Hz through the ffmpeg CLI (whisperx/audio.py:25-65)."""
+    cmd = ["ffmpeg", "-nostdin", "-threads", "0", "-i", file, "-f", "s16le", "-ac", "1",
+           "-acodec", "pcm_s16le", "-ar", str(sr), "-"]
+    try:
+        raw = subprocess.run(cmd, capture_output=True, check=True).stdout
+    except subprocess.CalledProcessError as e:
+        raise RuntimeError(f"Failed to load audio: {e.stderr.decode()}") from e
+    return np.frombuffer(raw, np.int16).flatten().astype(np.float32) / 32768.0
+
+
+def load_align_model(language_code, device, model_name=None, model_dir=None):
+    """alignment.py:64-97: pick (or take) a wav2vec2 CTC model, load it on `device`, and return
+    `(model, {"language", "dictionary", "type"})`.  The emission model stays a PyTorch module."""
+    import torchaudio
+    if model_name is None:
+        model_name = DEFAULT_ALIGN_MODELS_TORCH.get(language_code) or DEFAULT_ALIGN_MODELS_HF.get(language_code)
+        if model_name is None:
+            print(f"There is no default alignment model set for this language ({language_code}).\
+                Please find a wav2vec2.0 model finetuned on this language in https://huggingface.co/models, then pass the model name in --align_model [MODEL_NAME]")
+            raise ValueError(f"No default align-model for language: {language_code}")
+    if model_name in torchaudio.pipelines.__all__:
+        kind = "torchaudio"
+        bundle = getattr(torchaudio.pipelines, model_name)
+        model = bundle.get_model(dl_kwargs={"model_dir": model_dir}).to(device)
+        dictionary = {c.lower(): i for i, c in enumerate(bundle.get_labels())}
+    else:
+        from transformers import Wav2Vec2ForCTC, Wav2Vec2Processor
+        try:
+            processor = Wav2Vec2Processor.from_pretrained(model_name)
+            model = Wav2Vec2ForCTC.from_pretrained(model_name)
+        except Exception as e:
+            print(e)
+            print("Error loading model from huggingface, check https://huggingface.co/models for finetuned wav2vec2.0 models")
+            raise ValueError(f'The chosen align_model "{model_name}" could not be found in huggingface (https://huggingface.co/models) or torchaudio (https://pytorch.org/audio/stable/pipelines.html#id14)')
+        kind = "huggingface"
+        model = model.to(device)
+        dictionary = {ch.lower(): code for ch, code in processor.tokenizer.get_vocab().items()}
+    return model, {"language": language_code, "dictionary": dictionary, "type": kind}
+
+
+# --------------------------------------------------------------------------- emissions
+def _forward(model, model_type: str, wav: torch.Tensor, lengths):
+    if model_type == "torchaudio":
+        out, _ = model(wav, lengths=lengths)
+    elif model_type == "huggingface":
+        out = model(wav).logits
+    else:
+        raise NotImplementedError(f"Align model of type {model_type} not supported.")
+    return out
+
+
+def _emit(model, model_type: str, audio: torch.Tensor, jobs: list, device) -> list:
+    """wav2vec2 forward for every runnable segment (alignment.py:212-232); logits stay on `device`.
+    jobs: [(f1, f2)] sample ranges.  Returns one [T, V] float32 tensor per job and the channel count."""
+    outs: List[Optional[torch.Tensor]] = [None] * len(jobs)
+    with torch.inference_mode():
+        order = range(len(jobs))
+        groups: dict = {}
+        if EMISSION_BATCH > 1 and audio.shape[0] == 1:
+            for i in order:
+                f1, f2 = jobs[i]
+                n = min(f2, audio.shape[1]) - f1
+                if n >= 400:
+                    groups.setdefault(n, []).append(i)
+        batched = set()
+        for n, members in groups.items():
+            for k in range(0, len(members), EMISSION_BATCH):
+                part = members[k:k + EMISSION_BATCH]
+                if len(part) < 2:
+                    continue
+                wav = torch.stack([audio[0, jobs[i][0]:jobs[i][1]] for i in part]).to(device)
+                logits = _forward(model, model_type, wav, None)
+                for row, i in enumerate(part):
+                    outs[i] = logits[row].float()
+                    batched.add(i)
+        for i in order:
+            if i in batched:
+                continue
+            f1, f2 = jobs[i]
+            wav = audio[:, f1:f2]
+            lengths = None
+            if wav.shape[-1] < 400:                       # minimum wav2vec2 input (alignment.py:217-221)
+                lengths = torch.as_tensor([wav.shape[-1]]).to(device)
+                wav = torch.nn.functional.pad(wav, (0, 400 - wav.shape[-1]))
+            outs[i] = _forward(model, model_type, wav.to(device), lengths)[0].float()
+    return outs
+
+
+# --------------------------------------------------------------------------- align()
+def align(
+    transcript: Iterable[dict],
+    model: torch.nn.Module,
+    align_model_metadata: dict,
+    audio: Union[str, np.ndarray, torch.Tensor],
+    device: str,
+    interpolate_method: str = "nearest",
+    return_char_alignments: bool = False,
+    print_progress: bool = False,
+    combined_progress: bool = False,
+) -> dict:
+    """Align phoneme recognition predictions to known transcription (alignment.py:100-354).
+
+    Same arguments, side effects (the four keys added to every input segment) and result as the
+    reference; the per-segment "Failed to align segment" messages are printed for the same
+    three soft failures (:199-207, :245-248)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("whisperx_b200.align() runs the alignment path on a CUDA (sm_100a) device only; "
+                           f"got device={device!r}. There is no CPU fallback.")
+    engine = get_engine(dev)
+    dev = engine.device
+
+    if not torch.is_tensor(audio):
+        if isinstance(audio, str):
+            audio = load_audio(audio)
+        audio = torch.from_numpy(audio)
+    if len(audio.shape) == 1:
+        audio = audio.unsqueeze(0)
+    max_duration = audio.shape[1] / SAMPLE_RATE
+
+    dictionary = align_model_metadata["dictionary"]
+    lang = align_model_metadata["language"]
+    model_type = align_model_metadata["type"]
+    if model_type not in ("torchaudio", "huggingface"):
+        raise NotImplementedError(f"Align model of type {model_type} not supported.")
+
+    # 1. keep only characters the model knows (mutates the input, like the reference)
+    transcript = transcript if isinstance(transcript, list) else list(transcript)
+    assemble.prepare_transcript(transcript, dictionary, lang, print_progress, combined_progress)
+
+    # 2a. which segments reach the model (alignment.py:198-207)
+    plain: List[dict] = []
+    verdict: List[Optional[str]] = []
+    run: List[int] = []
+    for sdx, seg in enumerate(transcript):
+        rec = {"start": seg["start"], "end": seg["end"], "text": seg["text"], "words": []}
+        if return_char_alignments:
+            rec["chars"] = []
+        plain.append(rec)
+        if len(seg["clean_char"]) == 0:
+            verdict.append("no characters in this segment found in model dictionary, resorting to original...")
+        elif seg["start"] >= max_duration:
+            verdict.append("original start time longer than audio duration, skipping...")
+        else:
+            verdict.append(None)
+            run.append(sdx)
+
+    results: dict = {}
+    if run:
+        jobs = [(int(transcript[s]["start"] * SAMPLE_RATE), int(transcript[s]["end"] * SAMPLE_RATE)) for s in run]
+        logits = _emit(model, model_type, audio, jobs, dev)
+        results = _align_batch(engine, [transcript[s] for s in run], logits, dictionary, lang, audio.shape[0])
+
+    # 3. records, in input order
+    aligned: List[dict] = []
+    k = 0
+    for sdx, seg in enumerate(transcript):
+        why = verdict[sdx]
+        if why is None:
+            r = results["segments"][k]
+            k += 1
+            if r is None:
+                why = "backtrack failed, resorting to original..."
+            else:
+                lay, cs, ce, sc, ws, we, wsc = r
+                aligned += assemble.assemble_segment(seg["text"], seg["clean_cdx"], lay, seg["sentence_spans"], lang,
+                                                     cs, ce, sc, ws, we, wsc, interpolate_method, return_char_alignments)
+                continue
+        print(f'Failed to align segment ("{seg["text"]}"): {why}')
+        aligned.append(plain[sdx])
+
+    word_segments: List[dict] = []
+    for seg in aligned:
+        word_segments += seg["words"]
+    return {"segments": aligned, "word_segments": word_segments}
+
+
+def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], dictionary: dict, lang: str,
+                 channels: int) -> dict:
+    """One pass of the kernels over all runnable segments of the call (alignment.py:233-320)."""
+    dev = engine.device
+    S = len(segs)
+    V = int(logits[0].shape[-1])
+    blank = assemble.blank_id_of(dictionary)
+    frame_off = np.zeros(S + 1, np.int64)
+    frame_len = np.zeros(S, np.int32)
+    tok_off = np.zeros(S + 1, np.int64)
+    t1 = np.zeros(S, np.float64)
+    ratio = np.zeros(S, np.float64)
+    round_np = np.zeros(S, np.uint8)
+    word_off = np.zeros(S + 1, np.int64)
+    tokens: List[int] = []
+    wchar_off: List[int] = [0]
+    wchar_idx: List[int] = []
+    layouts = []
+    for s, seg in enumerate(segs):
+        T = int(logits[s].shape[0])
+        frame_len[s] = T
+        frame_off[s + 1] = frame_off[s] + T + (-T) % 4        # 4-row granules keep every segment 16-byte aligned
+        tokens += [dictionary[c] for c in seg["clean_char"]]
+        tok_off[s + 1] = len(tokens)
+        a, b = seg["start"], seg["end"]
+        t1[s] = a
+        ratio[s] = (b - a) * channels / T                      # alignment.py:252-253
+        round_np[s] = isinstance(a, np.floating) or isinstance(b, np.floating)
+        lay = assemble.layout_segment(seg["text"], seg["clean_cdx"], seg["sentence_spans"], lang)
+        layouts.append(lay)
+        base = len(wchar_idx)
+        wchar_idx += lay.group_idx
+        wchar_off += [base + o for o in lay.group_off[1:]]
+        word_off[s + 1] = len(wchar_off) - 1
+
+    emis = torch.zeros((int(frame_off[-1]), V), dtype=torch.float32, device=dev)
+    for s in range(S):
+        emis[int(frame_off[s]):int(frame_off[s]) + int(frame_len[s])] = logits[s]
+    if EMISSION_MODE not in ("fused", "torch", "logprobs"):
+        raise ValueError(f"WXB_EMISSION_MODE={EMISSION_MODE!r}: expected fused, torch or logprobs")
+    fused = EMISSION_MODE == "fused"
+    if EMISSION_MODE == "torch":
+        emis = torch.log_softmax(emis, dim=-1)
+    has_words = len(wchar_off) > 1
+    spec = BatchSpec(frame_off=frame_off, frame_len=frame_len, tok_off=tok_off, tokens=np.asarray(tokens, np.int32),
+                     vocab=V, blank_id=blank, logits=fused, seg_t1=t1, seg_ratio=ratio, seg_round_np=round_np,
+                     word_off=word_off if has_words else None,
+                     wchar_off=np.asarray(wchar_off, np.int64) if has_words else None,
+                     wchar_idx=np.asarray(wchar_idx, np.int32) if has_words else None)
+    res = engine.align_batch(emis, spec, want=("logprobs",) if (KEEP_LAST_BATCH and fused) else ())
+    if KEEP_LAST_BATCH:
+        LAST_BATCH.clear()
+        LAST_BATCH.update(spec=spec, result=res, emissions=emis)
+    status = res.status.cpu().tolist()
+    cs = res.char_start_s.cpu().tolist()
+    ce = res.char_end_s.cpu().tolist()
+    sc = res.char_score_r.cpu().tolist()
+    if has_words:
+        ws, we, wsc = res.word_start_s.cpu().tolist(), res.word_end_s.cpu().tolist(), res.word_score.cpu().tolist()
+    else:
+        ws = we = wsc = []
+    out = []
+    for s in range(S):
+        if status[s] != 0:
+            out.append(None)
+            continue
+        a, b = int(tok_off[s]), int(tok_off[s + 1])
+        g0, g1 = int(word_off[s]), int(word_off[s + 1])
+        out.append((layouts[s], cs[a:b], ce[a:b], sc[a:b], ws[g0:g1], we[g0:g1], wsc[g0:g1]))
+    return {"segments": out, "spec": spec, "result": res}
+
+
+# --------------------------------------------------------------------------- functional API
+@dataclass
+class Point:                               # alignment.py:381-385
+    token_index: int
+    time_index: int
+    score: float
+
+
+@dataclass
+class Segment:                             # alignment.py:424-436
+    label: str
+    start: int
+    end: int
+    score: float
+
+    def __repr__(self):
+        return f"{self.label}\t({self.score:4.2f}): [{self.start:5d}, {self.end:5d})"
+
+    @property
+    def length(self):
+        return self.end - self.start
+
+
+def _single_spec(emission: torch.Tensor, tokens: Sequence[int], blank_id: int, **kw) -> BatchSpec:
+    T, V = emission.shape
+    return BatchSpec(frame_off=[0, T], tok_off=[0, len(tokens)], tokens=np.asarray(tokens, np.int32), vocab=V,
+                     blank_id=blank_id, **kw)
+
+
+def get_trellis(emission: torch.Tensor, tokens: Sequence[int], blank_id: int = 0, device="cuda:0") -> torch.Tensor:
+    """alignment.py:359-379 — the full (T+1, N+1) float32 table, computed by the kernel's
+    introspection path (the batch path never materialises it).  Returned on the CPU like the
+    reference's."""
+    eng = get_engine(device)
+    E = emission.to(eng.device, torch.float32).contiguous()
+    spec = _single_spec(E, tokens, blank_id, no_shortcut=True)
+    res = eng.align_batch(E, spec, want=("trellis",))
+    return res.trellis[: (E.shape[0] + 1) * (len(tokens) + 1)].view(E.shape[0] + 1, len(tokens) + 1).cpu()
+
+
+def backtrack(trellis: torch.Tensor, emission: torch.Tensor, tokens: Sequence[int], blank_id: int = 0,
+              device="cuda:0") -> Optional[List[Point]]:
+    """alignment.py:387-421 from a caller-supplied trellis; None when the walk never reaches token 0."""
+    eng = get_engine(device)
+    status, _, ptok, plogp = eng.backtrack_trellis(trellis, emission, tokens, blank_id)
+    if status != 0:
+        return None
+    prob = torch.exp(plogp).double().tolist()
+    tok = ptok.tolist()
+    return [Point(tok[t], t, prob[t]) for t in range(len(tok)) if tok[t] >= 0]
+
+
+def merge_repeats(path: Sequence[Point], transcript: str) -> List[Segment]:
+    """alignment.py:438-454: one Segment per run of equal token_index, score = mean point score."""
+    out: List[Segment] = []
+    i = 0
+    while i < len(path):
+        j = i
+        total = 0
+        while j < len(path) and path[j].token_index == path[i].token_index:
+            total = total + path[j].score
+            j += 1
+        out.append(Segment(transcript[path[i].token_index], path[i].time_index, path[j - 1].time_index + 1,
+                           total / (j - i)))
+        i = j
+    return out
+
+
+def merge_words(segments: Sequence[Segment], separator: str = "|") -> List[Segment]:
+    """alignment.py:456-470 (unused by align(); kept for API parity): words are the runs between
+    separator labels, score = length-weighted mean of the character scores."""
+    words: List[Segment] = []
+    run: List[Segment] = []
+    for seg in list(segments) + [None]:
+        if seg is not None and seg.label != separator:
+            run.append(seg)
+            continue
+        if run:
+            weight = sum(s.length for s in run)
+            words.append(Segment("".join(s.label for s in run), run[0].start, run[-1].end,
+                                 sum(s.score * s.length for s in run) / weight))
+            run = []
+    return words

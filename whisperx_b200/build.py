@@ -22,6 +22,11 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: the reference adds and compares float32 values; no contraction anywhere.
 FLAGS = ARCH + ["-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE]
+if os.environ.get("WXB_EXTRA_NVCC_FLAGS"):            # experiments only (e.g. -DWXB_UNROLL=2)
+    FLAGS += os.environ["WXB_EXTRA_NVCC_FLAGS"].split()
+if os.environ.get("WXB_LIB_OUT"):
+    LIB = os.environ["WXB_LIB_OUT"]
+    OBJ = LIB + ".objs"
 RANGES = [(1, 8), (9, 16), (17, 24), (25, 32), (33, 40), (41, 48), (49, 56), (57, 64)]
 
 

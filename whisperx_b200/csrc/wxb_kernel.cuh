@@ -52,6 +52,9 @@ struct Params {
     unsigned long long *trace;   // debug: [4 * n_desc] {t_begin, t_forward_done, t_end, smid} per CTA, or null
 };
 
+#ifndef WXB_UNROLL
+#define WXB_UNROLL 2      // frames per unrolled block of the recurrence (must divide 32)
+#endif
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int SM_TAIL_BYTES = 144 + 256 + 16;   // col0[36] floats + xd[32] doubles + 2 mbarriers
 
@@ -304,9 +307,9 @@ __global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg
         };
 
         int tt = 0;
-        for (; tt + 8 <= n; tt += 8) {
+        for (; tt + WXB_UNROLL <= n; tt += WXB_UNROLL) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) step(tt + u);
+            for (int u = 0; u < WXB_UNROLL; ++u) step(tt + u);
             flush_if_word_done();
         }
         for (; tt < n; ++tt) {
