@@ -105,7 +105,7 @@ typedef struct wxb_outputs {
 
 typedef struct wxb_limits {
     int32_t max_vocab;          /* largest V the fused emission staging handles */
-    int32_t max_tokens;         /* largest N per segment */
+    int32_t max_tokens;         /* largest N per segment (32 lanes x max warps x max K) */
     int32_t tokens_per_lane;    /* largest K (token columns held in registers per lane) */
     int32_t sm_count;           /* SMs of the device the ctx was created on */
 } wxb_limits;
@@ -117,7 +117,7 @@ int  wxb_create(int device, wxb_ctx **out);             /* binds to CUDA device 
 void wxb_destroy(wxb_ctx *ctx);
 int  wxb_get_limits(const wxb_ctx *ctx, wxb_limits *out);
 
-/* ---- plan: validate + bucket by tokens-per-lane + cost-sort + upload descriptors ----
+/* ---- plan: validate + bucket by (warps, tokens-per-lane) + cost-sort + upload descriptors ----
  * Replaces the per-segment token lookup and loop set-up of alignment.py:182-210. */
 int  wxb_plan_create(wxb_ctx *ctx, const wxb_batch *batch, wxb_plan **out);
 void wxb_plan_destroy(wxb_plan *plan);
@@ -167,7 +167,11 @@ int  wxb_plan_debug_trace(wxb_plan *plan, uint64_t *rows, int64_t cap_rows);
 double wxb_round3(double x);                              /* Python round(x, 3) (alignment.py:262-264) */
 double wxb_round3_np(double x);                           /* np.float64.__round__(3) (alignment.py:308) */
 double wxb_pairwise_sum(const double *a, int64_t n);      /* numpy add.reduce order (alignment.py:308) */
-int    wxb_tokens_per_lane(int32_t n_tokens);             /* K bucket for N tokens, <=0 if unsupported */
+int    wxb_tokens_per_lane(int32_t n_tokens);             /* K (token columns per lane) for N tokens, <=0 if unsupported */
+int    wxb_segment_warps(int32_t n_tokens);               /* W (compute warps of the segment's CTA), <=0 if unsupported */
+/* Planner knob: a segment gets the fewest warps that keep K <= k_target (1..8, default 6).  Returns the
+ * previous value; k_target <= 0 only queries.  Process-wide; affects plans created afterwards. */
+int    wxb_set_k_target(int k_target);
 
 #ifdef __cplusplus
 }

@@ -35,9 +35,12 @@ def main():
     beg, fwd, end = (rows[:, 0] - t0) / 1e3, (rows[:, 1] - t0) / 1e3, (rows[:, 2] - t0) / 1e3
     print(f"rows={n} span={end.max():.1f} us  last begin={beg.max():.1f} us")
     K, T = rows[:, 6], rows[:, 4]
-    for k in sorted(set(K.tolist()), reverse=True):
-        m = K == k
-        print(f"K={k:2d} n={m.sum():4d} begin[{beg[m].min():7.1f},{beg[m].max():7.1f}] end max={end[m].max():7.1f} "
+    Wn = np.array([eng._lib.wxb_segment_warps(int(x)) for x in rows[:, 5]])
+    KW = Wn * 100 + K
+    for kw in sorted(set(KW.tolist()), reverse=True):
+        m = KW == kw
+        k = kw % 100
+        print(f"W={kw // 100} K={k:2d} n={m.sum():4d} begin[{beg[m].min():7.1f},{beg[m].max():7.1f}] end max={end[m].max():7.1f} "
               f"dur mean={np.mean(end[m]-beg[m]):7.1f} max={np.max(end[m]-beg[m]):7.1f}  fwd share={np.mean((fwd[m]-beg[m])/(end[m]-beg[m])):.2f} "
               f"ns/frame={np.mean((fwd[m]-beg[m])*1e3/T[m]):.0f}")
     # concurrency over time

@@ -134,7 +134,8 @@ def test_batched_emission_forward(wxa):
     assert len(one["segments"]) == len(four["segments"]) == 4
     # batched GEMMs may differ in the last bits; word timing on a random model can move by a frame
     for a, b in zip(one["word_segments"], four["word_segments"]):
-        assert a["word"] == b["word"] and abs(a["start"] - b["start"]) <= 0.0401
+        assert a["word"] == b["word"] and ("start" in a) == ("start" in b)
+        assert "start" not in a or abs(a["start"] - b["start"]) <= 0.0401
 
 
 def test_cpu_device_is_refused(wxa):

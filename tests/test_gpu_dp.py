@@ -101,15 +101,34 @@ def test_golden_reference_vectors(engine, golden_dp):
             assert torch.exp(pl).double().tolist() == arr[n + "_pscore"].tolist()
 
 
-@pytest.mark.parametrize("N", [1, 31, 32, 33, 64, 65, 95, 97, 416, 417, 512, 513, 700, 1023, 1025, 1500, 2047, 2048])
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 64, 65, 95, 97, 191, 192, 193, 256, 257, 384, 385, 416, 417, 512, 513, 576, 577,
+                               700, 1023, 1025, 1500, 2047, 2048, 3100])
 def test_every_token_bucket_boundary(engine, N):
-    """tokens-per-lane classes K=1..64 incl. the r=1 / r=32 lane splits."""
+    """(warps, tokens-per-lane) classes incl. the r=1 / r=32W lane splits and the 1->2->3 warp steps."""
     rng = np.random.default_rng(N)
     T = N + int(rng.integers(0, 120))
     cases = [(logprobs(rng, T, 29, ties=bool(N % 2)), rng.integers(0, 29, N).astype(np.int32))]
     small = N <= 700
     spec, res = run(engine, cases, 29, 0, align=4, want=("path", "final_col", "trellis") if small else ("path",))
     check_against_oracle(spec, res, cases, 0, full=small)
+
+
+@pytest.mark.parametrize("k_target", [1, 2, 3, 5, 7, 8])
+def test_k_target_sweep(engine, k_target):
+    """Every instantiated tokens-per-lane class (K = 1..8) and many warp counts, by moving the planner knob."""
+    from whisperx_b200 import _native
+    lib = _native.load()
+    rng = np.random.default_rng(100 + k_target)
+    cases = []
+    for N in (1, 5, 32, 33, 70, 128, 200, 257, 300, 449, 640, 900):
+        T = N + int(rng.integers(0, 150))
+        cases.append((logprobs(rng, T, 29, ties=bool(N % 2)), rng.integers(0, 29, N).astype(np.int32)))
+    old = lib.wxb_set_k_target(k_target)
+    try:
+        spec, res = run(engine, cases, 29, 0, align=4, want=("path", "final_col", "trellis"))
+    finally:
+        lib.wxb_set_k_target(old)
+    check_against_oracle(spec, res, cases, 0, full=True)
 
 
 def test_all_K_classes_one_batch(engine):

@@ -2,8 +2,7 @@
 
     python -m whisperx_b200.build [--force] [--verbose]
 
-The align kernel is instantiated for 64 tokens-per-lane classes; the instantiations are split
-over 8 translation units compiled in parallel.
+Two translation units (kernel instantiations, host side of the C ABI) compiled in parallel.
 """
 from __future__ import annotations
 
@@ -27,7 +26,6 @@ if os.environ.get("WXB_EXTRA_NVCC_FLAGS"):            # experiments only (e.g. -
 if os.environ.get("WXB_LIB_OUT"):
     LIB = os.environ["WXB_LIB_OUT"]
     OBJ = LIB + ".objs"
-RANGES = [(1, 8), (9, 16), (17, 24), (25, 32), (33, 40), (41, 48), (49, 56), (57, 64)]
 
 
 def _nvcc() -> str:
@@ -48,10 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     jobs = []
-    for lo, hi in RANGES:
-        obj = os.path.join(OBJ, f"inst_{lo:02d}_{hi:02d}.o")
-        jobs.append((obj, [nvcc] + FLAGS + [f"-DWXB_KLO={lo}", f"-DWXB_KHI={hi}", "-c",
-                                           os.path.join(CSRC, "wxb_inst.cu"), "-o", obj]))
+    inst_obj = os.path.join(OBJ, "wxb_inst.o")
+    jobs.append((inst_obj, [nvcc] + FLAGS + ["-c", os.path.join(CSRC, "wxb_inst.cu"), "-o", inst_obj]))
     main_obj = os.path.join(OBJ, "wxb_align.o")
     jobs.append((main_obj, [nvcc] + FLAGS + ["-c", os.path.join(CSRC, "wxb_align.cu"), "-o", main_obj]))
 

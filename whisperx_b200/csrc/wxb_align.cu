@@ -15,29 +15,10 @@
 #include <vector>
 
 namespace wxb {
-#define WXB_DECL_RANGE(lo) \
-    cudaError_t launch_range_##lo(int k, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug);
-WXB_DECL_RANGE(1) WXB_DECL_RANGE(9) WXB_DECL_RANGE(17) WXB_DECL_RANGE(25)
-WXB_DECL_RANGE(33) WXB_DECL_RANGE(41) WXB_DECL_RANGE(49) WXB_DECL_RANGE(57)
-#undef WXB_DECL_RANGE
+cudaError_t launch_align(int k, int warps, int nb, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug);
 
-constexpr int KMAX = 64;
 constexpr int NSIDE = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
-
-static cudaError_t launch_k(int k, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
-    switch ((k - 1) / 8) {
-        case 0: return launch_range_1(k, p, first, count, smem, st, debug);
-        case 1: return launch_range_9(k, p, first, count, smem, st, debug);
-        case 2: return launch_range_17(k, p, first, count, smem, st, debug);
-        case 3: return launch_range_25(k, p, first, count, smem, st, debug);
-        case 4: return launch_range_33(k, p, first, count, smem, st, debug);
-        case 5: return launch_range_41(k, p, first, count, smem, st, debug);
-        case 6: return launch_range_49(k, p, first, count, smem, st, debug);
-        case 7: return launch_range_57(k, p, first, count, smem, st, debug);
-        default: return cudaErrorInvalidValue;
-    }
-}
 
 // ------------------------------------------------------------------ small kernels
 struct ShortSeg { long long tok_base; long long frame_base; int N; int T; int seg; int pad; };
@@ -292,14 +273,13 @@ struct wxb_ctx {
     DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
 };
 
-struct Bucket { int K; int first; int count; long long cost; };
+struct Bucket { int K; int W; int NB; size_t smem; int first; int count; long long cost; int maxT; };
 
 struct wxb_plan {
     wxb_ctx *ctx = nullptr;
     int64_t S = 0, W = 0, sum_T = 0, sum_N = 0;
     int V = 0, blank = 0, TE = 32;
     uint32_t flags = 0;
-    size_t smem = 0;
     bool has_sec = false, has_words = false, has_round_np = false;
     std::vector<Bucket> buckets;
     int n_short = 0;
@@ -315,27 +295,44 @@ struct wxb_plan {
     }
 };
 
-static int tokens_per_lane(long long n) {
-    if (n <= 0) return 0;
-    const long long k = (n + 31) / 32;
-    return k > KMAX ? -1 : static_cast<int>(k);
+// Warps and tokens-per-lane for a transcript of n tokens: as few compute warps as keep K <= k_target
+// (more columns per lane amortise the per-frame overhead; more warps shorten the segment's latency).
+static int g_k_target = 6;
+
+static bool shape_of(long long n, int *W, int *K) {
+    if (n <= 0) return false;
+    long long w = (n + 32ll * g_k_target - 1) / (32ll * g_k_target);
+    if (w > WMAX) w = WMAX;
+    const long long k = (n + 32 * w - 1) / (32 * w);
+    if (k > KMAX) return false;
+    *W = static_cast<int>(w);
+    *K = static_cast<int>(k);
+    return true;
 }
 
-static int pick_tile(int V, int *TE, size_t *smem) {
-    // Frames per shared-memory tile.  cp.async.bulk needs 16-byte multiples, i.e. TE % 4 == 0.
-    // Prefer the longest tile whose double buffer stays <= 16 KB (28+ resident warps per SM);
-    // a wide vocabulary falls back to 8, then 4 frames per tile as long as it fits at all.
-    const int pref[3] = {32, 16, 8};
-    for (int i = 0; i < 3; ++i) {
-        const size_t bytes = 2ull * pref[i] * V * 4 + SM_TAIL_BYTES;
-        if (bytes <= 16 * 1024) { *TE = pref[i]; *smem = bytes; return 0; }
-    }
-    const int last[2] = {8, 4};
-    for (int i = 0; i < 2; ++i) {
-        const size_t bytes = 2ull * last[i] * V * 4 + SM_TAIL_BYTES;
-        if (bytes <= static_cast<size_t>(SMEM_LIMIT)) { *TE = last[i]; *smem = bytes; return 0; }
+static int tokens_per_lane(long long n) {
+    int W, K;
+    if (n <= 0) return 0;
+    return shape_of(n, &W, &K) ? K : -1;
+}
+
+// Frames per shared-memory tile (cp.async.bulk needs 16-byte multiples, i.e. TE % 4 == 0): 32 when the
+// widest CTA of the batch still fits a ring of at least 2 tiles, else 16, 8, 4.
+static int pick_tile(int V, int Wmax, int *TE) {
+    const int pref[4] = {32, 16, 8, 4};
+    for (int i = 0; i < 4; ++i) {
+        if (smem_layout(Wmax, 2, pref[i], V).total <= static_cast<uint32_t>(SMEM_LIMIT)) { *TE = pref[i]; return 0; }
     }
     return -1;
+}
+
+// Ring depth for a W-warp CTA: W + 2 lets the producer run one tile ahead of a fully staggered
+// wavefront; fewer if shared memory says so (any depth >= 2 is deadlock-free).
+static int pick_ring(int W, int TE, int V, size_t *smem) {
+    int nb = W + 2;
+    while (nb > 2 && smem_layout(W, nb, TE, V).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
+    *smem = smem_layout(W, nb, TE, V).total;
+    return nb;
 }
 
 // ------------------------------------------------------------------ ABI: lifecycle
@@ -347,6 +344,16 @@ extern "C" double wxb_pairwise_sum(const double *a, int64_t n) {
     return wxb::pairwise_sum([&](long i) { return a[i]; }, static_cast<long>(n));
 }
 extern "C" int wxb_tokens_per_lane(int32_t n_tokens) { return tokens_per_lane(n_tokens); }
+extern "C" int wxb_segment_warps(int32_t n_tokens) {
+    int W, K;
+    if (n_tokens <= 0) return 0;
+    return shape_of(n_tokens, &W, &K) ? W : -1;
+}
+extern "C" int wxb_set_k_target(int k_target) {
+    const int old = g_k_target;
+    if (k_target > 0) g_k_target = std::max(1, std::min(KMAX, k_target));
+    return old;
+}
 
 extern "C" int wxb_create(int device, wxb_ctx **out) {
     if (!out) return fail(WXB_EINVAL, "wxb_create: out is NULL");
@@ -364,6 +371,7 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     c->device = device;
     if (const char *e = getenv("WXB_SIDE_STREAMS")) c->side_streams = std::max(1, std::min(NSIDE, atoi(e)));
     if (const char *e = getenv("WXB_TRACE")) c->want_trace = atoi(e) != 0;
+    if (const char *e = getenv("WXB_K_TARGET")) g_k_target = std::max(1, std::min(KMAX, atoi(e)));
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
     for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
@@ -400,8 +408,10 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
 
 extern "C" int wxb_get_limits(const wxb_ctx *ctx, wxb_limits *out) {
     if (!ctx || !out) return fail(WXB_EINVAL, "wxb_get_limits: NULL argument");
-    out->max_vocab = (SMEM_LIMIT - SM_TAIL_BYTES) / (2 * 4 * 4);
-    out->max_tokens = 32 * KMAX;
+    int vmax = 1;
+    while (smem_layout(1, 2, 4, vmax + 1).total <= static_cast<uint32_t>(SMEM_LIMIT)) ++vmax;
+    out->max_vocab = vmax;
+    out->max_tokens = 32 * WMAX * KMAX;
     out->tokens_per_lane = KMAX;
     out->sm_count = ctx->sm_count;
     return WXB_OK;
@@ -440,8 +450,6 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
     pl->has_sec = bt->seg_t1 != nullptr;
     pl->W = bt->n_words;
     pl->has_words = bt->n_words > 0;
-    if (pick_tile(pl->V, &pl->TE, &pl->smem) != 0)
-        return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory per tile", pl->V, SMEM_LIMIT);
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (S == 0) { guard.p = nullptr; *out = pl; return WXB_OK; }
 
@@ -465,6 +473,7 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
     std::vector<ShortSeg> shorts;
     std::vector<long long> seg_tok_base(static_cast<size_t>(S));
     long long trellis_off = 0;
+    int wmax = 1;
     const bool no_shortcut = (bt->flags & WXB_F_NO_SHORTCUT) != 0;
     for (int64_t s = 0; s < S; ++s) {
         const int T = bt->frame_len ? bt->frame_len[s] : static_cast<int>(fo[s + 1] - fo[s]);
@@ -472,38 +481,48 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
         seg_tok_base[s] = to[s];
         const long long this_trellis = trellis_off;
         trellis_off += static_cast<long long>(T + 1) * (N + 1);
-        const int K = tokens_per_lane(N);
-        if (N == 0 || (N > T && (!no_shortcut || K < 0))) {
+        int K = -1, Wc = 0;
+        const bool fits = shape_of(N, &Wc, &K);
+        if (N == 0 || (N > T && (!no_shortcut || !fits))) {
             shorts.push_back({to[s], fo[s], N, T, static_cast<int>(s), 0});
             continue;
         }
-        if (K < 0)
-            return fail(WXB_EUNSUPPORTED, "wxb_plan_create: segment %lld has %d tokens; this build aligns at most %d per segment", (long long)s, N, 32 * KMAX);
+        if (!fits)
+            return fail(WXB_EUNSUPPORTED, "wxb_plan_create: segment %lld has %d tokens; this build aligns at most %d per segment", (long long)s, N, 32 * WMAX * KMAX);
         SegDesc d;
         d.emis_off = fo[s] * static_cast<long long>(pl->V);
         d.frame_base = fo[s];
         d.tok_base = to[s];
         d.bits_off = 0;
         d.trellis_off = this_trellis;
-        d.T = T; d.N = N; d.seg = static_cast<int>(s); d.K = K;
+        d.T = T; d.N = N; d.seg = static_cast<int>(s); d.K = K; d.W = Wc; d.pad = 0;
+        wmax = std::max(wmax, Wc);
         descs.push_back(d);
         pl->cells += static_cast<long long>(T) * N;
         pl->alg_bytes += 4ll * T * pl->V + 20ll * N;
     }
     pl->trellis_floats = trellis_off;
     pl->n_short = static_cast<int>(shorts.size());
-    // longest-first inside a bucket: the block scheduler hands out CTAs in index order (LPT)
+    if (pick_tile(pl->V, wmax, &pl->TE) != 0)
+        return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory for a %d-warp segment", pl->V, SMEM_LIMIT, wmax);
+    // one launch per (warps, tokens-per-lane) class; longest-first inside a class: the block
+    // scheduler hands out CTAs in index order (LPT)
     std::stable_sort(descs.begin(), descs.end(), [](const SegDesc &a, const SegDesc &b) {
+        if (a.W != b.W) return a.W > b.W;
         if (a.K != b.K) return a.K > b.K;
         return a.T > b.T;
     });
     long long bits = 0;
     for (size_t i = 0; i < descs.size(); ++i) {
         descs[i].bits_off = bits;
-        bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].K * 32;
-        if (i == 0 || descs[i].K != descs[i - 1].K) pl->buckets.push_back({descs[i].K, static_cast<int>(i), 0, 0});
+        bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].W * descs[i].K * 32;
+        if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W) {
+            Bucket b{descs[i].K, descs[i].W, 0, 0, static_cast<int>(i), 0, 0, descs[i].T};
+            b.NB = pick_ring(b.W, pl->TE, pl->V, &b.smem);
+            pl->buckets.push_back(b);
+        }
         pl->buckets.back().count += 1;
-        pl->buckets.back().cost += static_cast<long long>(descs[i].T) * descs[i].K;
+        pl->buckets.back().cost += static_cast<long long>(descs[i].T) * descs[i].K * descs[i].W;
     }
     pl->bits_words = bits;
     std::vector<FinBlock> fin;
@@ -512,7 +531,12 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
     pl->n_fin_blocks = static_cast<int>(fin.size());
     pl->n_desc = static_cast<int>(descs.size());
     pl->host_descs = descs;
-    std::stable_sort(pl->buckets.begin(), pl->buckets.end(), [](const Bucket &a, const Bucket &b) { return a.cost > b.cost; });
+    // launch order = placement priority: classes holding the longest segments go first (LPT across
+    // classes; a segment's latency grows with its frame count, not with its class's total cost)
+    std::stable_sort(pl->buckets.begin(), pl->buckets.end(), [](const Bucket &a, const Bucket &b) {
+        if (a.maxT != b.maxT) return a.maxT > b.maxT;
+        return a.cost > b.cost;
+    });
 
     // ---- upload ----
     std::vector<int> tok4(static_cast<size_t>(std::max<int64_t>(pl->sum_N, 1)));
@@ -633,7 +657,7 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     const int nb = static_cast<int>(pl->buckets.size());
     if (nb == 1) {
         const Bucket &b = pl->buckets[0];
-        CUDA_TRY(launch_k(b.K, P, b.first, b.count, pl->smem, st, debug));
+        CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, st, debug));
     } else if (nb > 1) {
         // buckets are independent: fork onto side streams so that every SM sees a mix of K classes
         const int used = std::min(nb, c->side_streams);
@@ -641,7 +665,7 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
         for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
         for (int i = 0; i < nb; ++i) {
             const Bucket &b = pl->buckets[i];
-            CUDA_TRY(launch_k(b.K, P, b.first, b.count, pl->smem, c->side[i % used], debug));
+            CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, c->side[i % used], debug));
         }
         for (int i = 0; i < used; ++i) {
             CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));

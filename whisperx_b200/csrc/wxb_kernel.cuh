@@ -1,18 +1,30 @@
-// Fused forced-alignment kernel for sm_100a: one warp (= one CTA) per transcript segment.
+// Fused forced-alignment kernel for sm_100a: one CTA per transcript segment, the token axis of
+// the trellis split over the CTA's warps and swept as a wavefront.
 //
 // Replaces, for a whole batch of segments, the reference's per-segment Python:
-//   log_softmax            whisperx/alignment.py:233      (fused into the tile staging, optional)
-//   get_trellis            whisperx/alignment.py:359-379  (phase 1: recurrence, token axis in registers)
-//   backtrack              whisperx/alignment.py:387-421  (phase 2: walk over packed choice bits)
+//   log_softmax            whisperx/alignment.py:233      (producer warp, fused into the tile staging)
+//   get_trellis            whisperx/alignment.py:359-379  (compute warps: recurrence, token axis in registers)
+//   backtrack              whisperx/alignment.py:387-421  (last compute warp: walk over packed choice bits)
 //   merge_repeats          whisperx/alignment.py:438-454  (finalize_kernel: per-token start/end/mean prob)
 //   char timestamps        whisperx/alignment.py:252-264  (finalize_kernel: exact decimal rounding)
 //
-// Data movement: the segment's emission rows [T,V] are streamed HBM -> shared memory exactly once,
-// TE frames per tile, double buffered, with one cp.async.bulk (TMA bulk copy, mbarrier completion)
-// per tile when the rows are 16-byte aligned and 4-byte cp.async otherwise.  Nothing else of size
-// O(T*V) or O(T*N*4) ever exists: the trellis lives in registers (K token columns per lane), and
-// what backtrack needs is a 1-bit-per-cell stay/change matrix (T*N/8 bytes, L2 resident) plus
-// the running first-argmax of the last column.
+// CTA = W compute warps + 1 producer warp.  Global lane g = 32*w + lane owns K (g < r) or K-1
+// (g >= r) consecutive token columns, K = ceil(N / 32W) <= 8, so every lane of every warp holds real
+// columns and the last column of the transcript is always the last column of lane 31 of warp W-1.
+//
+//   producer warp   streams the segment's emission rows HBM -> shared memory exactly once, TE frames
+//                   per tile through a ring of NB buffers (one cp.async.bulk per tile, mbarrier
+//                   completion), applies log_softmax in place (one row per lane), and builds trellis
+//                   column 0 for the tile (float64 running sum of literal vocabulary column 0).
+//   compute warp w  runs the recurrence over its 32 lanes x K columns for the tile; the column to the
+//                   left of lane 0 comes from a per-tile boundary array in shared memory — column 0
+//                   for warp 0, the last column of warp w-1 otherwise — and lane 31 writes its own
+//                   last column into the boundary array of warp w+1.  Warp w therefore trails warp
+//                   w-1 by one tile: a systolic wavefront; handshakes are mbarriers, once per tile.
+//
+// Nothing of size O(T*V) or O(T*N*4) is ever written: the trellis lives in registers, and what the
+// backtrack needs is a 1-bit-per-cell stay/change matrix (T*N/8 bytes, L2 resident) plus the running
+// first-argmax of the last column.
 //
 // Exactness: float32 add / NaN-propagating max in the reference's order, no
 // FMA (-fmad=false; the recurrence has no multiply anyway), column 0 = float(double cumsum) of
@@ -30,6 +42,7 @@ struct SegDesc {
     long long bits_off;     // 32-bit word offset into the choice-bit scratch
     long long trellis_off;  // float offset into the debug trellis (DEBUG only)
     int T, N, seg, K;
+    int W, pad;             // compute warps of the segment's CTA
 };
 
 struct Params {
@@ -37,7 +50,7 @@ struct Params {
     const int *tokens;      // [sum_N] token ids
     const int *tok4;        // [sum_N] token ids * 4 (byte offset inside an emission row)
     const SegDesc *segs;
-    uint32_t *bits;         // [sum ceil(T/32)*K*32] choice words: word (w,slot,lane), bit 31-(t%32)
+    uint32_t *bits;         // choice words of a segment: word ((t/32)*W*K + w*K + slot)*32 + lane, bit 31-(t%32)
     float *p0;              // [sum_T] expf(logp[t, 0])
     float *rowmax;          // [sum_T] (logits mode) row max
     float *rowlse;          // [sum_T] (logits mode) log(sum(exp(x - max)))
@@ -53,10 +66,26 @@ struct Params {
 };
 
 #ifndef WXB_UNROLL
-#define WXB_UNROLL 2      // frames per unrolled block of the recurrence (must divide 32)
+#define WXB_UNROLL 4      // frames per unrolled block of the recurrence (must divide the tile length)
 #endif
 constexpr uint32_t FULL = 0xffffffffu;
-constexpr int SM_TAIL_BYTES = 144 + 256 + 16;   // col0[36] floats + xd[32] doubles + 2 mbarriers
+constexpr int KMAX = 8;          // largest tokens-per-lane class that is instantiated
+constexpr int WMAX = 31;         // compute warps per CTA (+1 producer warp = 1024 threads)
+
+// Shared-memory carve-up of one CTA (all offsets in bytes from the dynamic smem base).
+struct SmemLayout {
+    uint32_t tile_bytes, off_left, off_xd, off_fin, off_bar, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int W, int NB, int TE, int V) {
+    SmemLayout L;
+    L.tile_bytes = static_cast<uint32_t>(TE) * V * 4u;                    // TE % 4 == 0 -> multiple of 16
+    L.off_left = static_cast<uint32_t>(NB) * L.tile_bytes;                // left[W+1][NB][TE] float2 {boundary, blank}
+    L.off_xd = (L.off_left + static_cast<uint32_t>(W + 1) * NB * TE * 8u + 15u) & ~15u;   // 32 doubles
+    L.off_fin = L.off_xd + 256u;                                          // trellis[T, N] (one float)
+    L.off_bar = L.off_fin + 16u;                                          // tma[NB] full[NB] empty[NB] edge[W][NB]
+    L.total = L.off_bar + static_cast<uint32_t>(3 + W) * NB * 8u;
+    return L;
+}
 
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -71,6 +100,14 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
 // torch.maximum: NaN-propagating max in one FMNMX.NAN
 __device__ __forceinline__ float fmax_nan(float a, float b) {
     float r;
@@ -83,12 +120,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
@@ -101,249 +141,335 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+
+// token k (0-based) -> owning global lane / register slot: the first r global lanes hold K columns,
+// the rest K-1
+template <int K>
+__device__ __forceinline__ void owner_of(int k, int r, int &g, int &slot) {
+    if (K == 1 || k < r * K) { g = k / K; slot = k - g * K; }
+    else { const int kk = k - r * K; const int q = kk / (K > 1 ? K - 1 : 1); g = r + q; slot = kk - q * (K - 1); }
 }
 
-// token k (0-based) -> owning lane / register slot, for the "r lanes hold K columns, the rest K-1" split
-template <int K>
-__device__ __forceinline__ void owner_of(int k, int r, int &ln, int &slot) {
-    if (K == 1 || k < r * K) { ln = k / K; slot = k - ln * K; }
-    else { const int kk = k - r * K; const int q = kk / (K > 1 ? K - 1 : 1); ln = r + q; slot = kk - q * (K - 1); }
-}
+// Register budget per thread: the recurrence keeps 3K values live (state, choice accumulators, token
+// offsets) plus ~2K transients; a CTA of up to 1024 threads needs <= 64.  Fewer registers = more
+// resident warps to hide the dependent-issue latency of the recurrence.
+#ifndef WXB_REGS
+#define WXB_REGS(K) ((K) <= 4 ? 40 : (K) <= 6 ? 56 : 64)
+#endif
 
 template <int K, bool DEBUG>
-__global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg_first) {
+__global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params p, const int seg_first, const int NB) {
     extern __shared__ __align__(128) unsigned char sm[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform (uniform registers for the
+    // tile / barrier addresses derived from it)
+    const int wi = __shfl_sync(FULL, static_cast<int>(threadIdx.x >> 5), 0);
+    const int W = (blockDim.x >> 5) - 1;            // compute warps; warp W is the producer
     const SegDesc d = p.segs[seg_first + blockIdx.x];
     const int T = d.T, N = d.N, V = p.V, TE = p.TE;
-    if (p.trace && lane == 0) {
+    if (p.trace && threadIdx.x == 0) {
         uint32_t smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         p.trace[4ll * (seg_first + blockIdx.x) + 0] = global_ns();
         p.trace[4ll * (seg_first + blockIdx.x) + 3] = smid;
     }
-    const uint32_t tile_bytes = static_cast<uint32_t>(TE * V) * 4u;
-    float *col0_s = reinterpret_cast<float *>(sm + 2 * tile_bytes);
-    double *xd_s = reinterpret_cast<double *>(sm + 2 * tile_bytes + 144);
+    const SmemLayout L = smem_layout(W, NB, TE, V);
     const uint32_t sm_base = smem_u32(sm);
-    const uint32_t bar0 = sm_base + 2 * tile_bytes + 144 + 256;
-
-    // ---- column ownership: lanes [0,r) hold K token columns, lanes [r,32) hold K-1 ----
-    const int r = N - 32 * (K - 1);                 // 1..32 by construction of the K bucket
-    const bool wide = lane < r;
-    const int cb = wide ? lane * K : r * K + (lane - r) * (K - 1);
-    const int ncols = wide ? K : K - 1;
-    const int laneN = (K == 1) ? (N - 1) : 31;      // lane whose last real column is column N
-
-    uint32_t tokoff[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        // byte offsets (token*4) come pre-multiplied from the plan: a shift visible in PTX makes
-        // ptxas emit one LEA per cell per frame instead of folding LDS [R + UR] (row base is uniform)
-        tokoff[i] = (i < ncols) ? static_cast<uint32_t>(__ldg(p.tok4 + d.tok_base + cb + i)) : 0u;
-    }
-    float R[K];
-    uint32_t acc[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) { R[i] = -INFINITY; acc[i] = 0u; }   // trellis[0, 1:] = -inf  (:369)
-    float src = -INFINITY;          // this lane's last real column at the current row
-    float best = -INFINITY;         // running max of trellis[:, N]; trellis[0, N] = -inf
-    int bestt = 0;                  // first argmax (torch.argmax, :396)
-    double cum = 0.0;               // float64 running sum of logp[:, 0]  (torch.cumsum, :368)
-    const int infstart = T + 1 - N; // rows >= infstart of column 0 are +inf (:370)
-
-    const float *Eg = p.emis + d.emis_off;
-    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(Eg) & 15) == 0);
+    const uint32_t bar_tma = sm_base + L.off_bar;
+    const uint32_t bar_full = bar_tma + 8u * NB;
+    const uint32_t bar_empty = bar_full + 8u * NB;
+    const uint32_t bar_edge = bar_empty + 8u * NB;     // [w][b], w = 0..W-1 (row 0 unused)
+    const uint32_t left_stride_w = static_cast<uint32_t>(NB) * TE * 8u;   // bytes between left[w] and left[w+1]
     const int ntiles = (T + TE - 1) / TE;
+    const float *Eg = p.emis + d.emis_off;
 
-    if (lane == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < (3 + W) * NB; ++i) mbar_init(bar_tma + 8u * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    fence_proxy_async();
-    __syncwarp();
-
-    uint32_t phase_bits = 0;        // bit b = parity to wait for on buffer b
-    uint32_t bulk_bits = 0;         // bit b = buffer b was filled by a bulk copy
-
-    auto issue_tile = [&](int tau, int b) {
-        const int t0 = tau * TE;
-        const int n = min(TE, T - t0);
-        const float *srcp = Eg + static_cast<size_t>(t0) * V;
-        const uint32_t dst = sm_base + b * tile_bytes;
-        const uint32_t bytes = static_cast<uint32_t>(n * V) * 4u;
-        if (bulk_ok && (bytes & 15u) == 0u) {
-            if (lane == 0) {
-                fence_proxy_async();            // earlier generic reads/writes of this buffer
-                mbar_expect_tx(bar0 + 8 * b, bytes);
-                bulk_g2s(dst, srcp, bytes, bar0 + 8 * b);
-            }
-            bulk_bits |= (1u << b);
-        } else {
-            for (int i = lane; i < n * V; i += 32) cp_async4(dst + 4u * i, srcp + i);
-            bulk_bits &= ~(1u << b);
-        }
-    };
-
     if (DEBUG) {
         float *tr = p.trellis + d.trellis_off;
-        for (int j = lane; j <= N; j += 32)
-            tr[j] = (j == 0) ? ((infstart <= 0) ? INFINITY : 0.0f) : -INFINITY;
+        const int infstart0 = T + 1 - N;
+        for (int j = threadIdx.x; j <= N; j += blockDim.x)
+            tr[j] = (j == 0) ? ((infstart0 <= 0) ? INFINITY : 0.0f) : -INFINITY;
+        if (p.final_col && threadIdx.x == 0) p.final_col[d.frame_base + d.seg] = -INFINITY;
     }
-    if (DEBUG && p.final_col && lane == 0) p.final_col[d.frame_base + d.seg] = -INFINITY;
+    fence_proxy_async();
+    __syncthreads();
 
-    if (ntiles > 0) issue_tile(0, 0);
+    int t_start = 0;                // first argmax of trellis[:, N]; meaningful in the producer warp after the forward pass
+    float best_val = -INFINITY;
 
-    int t = 0;                      // frames consumed so far == current trellis row
-    for (int tau = 0; tau < ntiles; ++tau) {
-        const int b = tau & 1;
-        const int t0 = tau * TE;
-        const int n = min(TE, T - t0);
-        // ---- wait for tile tau, prefetch tile tau+1 into the other buffer ----
-        if (bulk_bits & (1u << b)) {
-            mbar_wait(bar0 + 8 * b, (phase_bits >> b) & 1u);
-            phase_bits ^= (1u << b);
-        } else {
-            cp_async_wait_all();
-        }
-        __syncwarp();
-        if (tau + 1 < ntiles) issue_tile(tau + 1, b ^ 1);
+    if (wi == W) {
+        // ================================================================ producer warp
+        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(Eg) & 15) == 0);
+        double *xd_s = reinterpret_cast<double *>(sm + L.off_xd);
+        double cum = 0.0;               // float64 running sum of logp[:, 0]  (torch.cumsum, :368)
+        const int infstart = T + 1 - N; // rows >= infstart of column 0 are +inf (:370)
 
-        float *tb = reinterpret_cast<float *>(sm + b * tile_bytes);
-        // ---- kernel (i), fused: log_softmax of the tile rows in place (one row per lane) ----
-        if (p.is_logits) {
-            if (lane < n) {
-                float *row = tb + lane * V;
-                float m, ls;
-                row_lse([&](int v) { return row[v]; }, V, m, ls);
-                for (int v = 0; v < V; ++v) row[v] = logp_from(row[v], m, ls);
-                p.rowmax[d.frame_base + t0 + lane] = m;
-                p.rowlse[d.frame_base + t0 + lane] = ls;
+        // ring position of the tile being issued (bi, lap parity pi) and processed (b, ph): plain
+        // counters instead of tau % NB, tau / NB keep the addresses in uniform registers
+        int bi = 0;
+        uint32_t pi = 0, lap = 0;
+        // Running first-argmax of trellis[:, N] (torch.argmax, :396).  The last compute warp leaves the
+        // rows a tile started from in the boundary array of the warp that would follow it; the
+        // producer folds them in, tile by tile in frame order, when it takes the ring slot back.
+        float best = -INFINITY;         // trellis[0, N] = -inf
+        int bestt = 0;
+        int sb = 0, st0 = 0;            // ring slot and first row of the next tile to scan
+        uint32_t sph = 0;
+        auto scan_next = [&]() {
+            mbar_wait(bar_empty + 8u * sb, sph);
+            const float2 *fin = reinterpret_cast<const float2 *>(sm + L.off_left) + (W * NB + sb) * TE;
+            float v = (st0 + lane < T && lane < TE) ? fin[lane].x : -INFINITY;
+            int vi = st0 + lane;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, v, off);
+                const int oi = __shfl_xor_sync(FULL, vi, off);
+                if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
             }
+            if (v > best) { best = v; bestt = vi; }
+            st0 += TE;
+            ++sb;
+            const bool wraps = (sb == NB);
+            sb = wraps ? 0 : sb;
+            sph ^= wraps ? 1u : 0u;
             __syncwarp();
-            if (p.logprobs) {
-                float *lp = p.logprobs + (d.frame_base + t0) * static_cast<long long>(V);
-                for (int i = lane; i < n * V; i += 32) lp[i] = tb[i];
+        };
+        auto issue = [&](int tau) -> bool {     // start the copy of tile tau into its ring buffer
+            const int b = bi;
+            if (lap) scan_next();               // waits until the last compute warp is done with the slot's previous tile
+            ++bi;
+            const bool wrapi = (bi == NB);
+            bi = wrapi ? 0 : bi;
+            pi ^= wrapi ? 1u : 0u;
+            lap |= wrapi ? 1u : 0u;
+            const int t0 = tau * TE;
+            const int n = min(TE, T - t0);
+            const float *srcp = Eg + static_cast<size_t>(t0) * V;
+            const uint32_t dst = sm_base + b * L.tile_bytes;
+            const uint32_t bytes = static_cast<uint32_t>(n * V) * 4u;
+            if (bulk_ok && (bytes & 15u) == 0u) {
+                if (lane == 0) {
+                    fence_proxy_async();            // earlier generic reads/writes of this buffer
+                    mbar_expect_tx(bar_tma + 8u * b, bytes);
+                    bulk_g2s(dst, srcp, bytes, bar_tma + 8u * b);
+                }
+                return true;
             }
-        }
-        // ---- column 0 of the trellis for rows t0 .. t0+n (exclusive float64 prefix) ----
-        {
+            float *tb = reinterpret_cast<float *>(sm + b * L.tile_bytes);
+            for (int i = lane; i < n * V; i += 32) tb[i] = __ldg(srcp + i);
+            return false;
+        };
+
+        bool cur_bulk = (ntiles > 0) ? issue(0) : false;
+        int b = -1;
+        uint32_t ph = 0;
+        for (int tau = 0; tau < ntiles; ++tau) {
+            ++b;
+            const bool wrap = (b == NB);
+            b = wrap ? 0 : b;
+            ph ^= wrap ? 1u : 0u;
+            const int t0 = tau * TE;
+            const int n = min(TE, T - t0);
+            bool next_bulk = false;
+            if (tau + 1 < ntiles) next_bulk = issue(tau + 1);
+            if (cur_bulk) mbar_wait(bar_tma + 8u * b, ph);
+            cur_bulk = next_bulk;
+            __syncwarp();
+            float *tb = reinterpret_cast<float *>(sm + b * L.tile_bytes);
+            // ---- kernel (i), fused: log_softmax of the tile rows in place (one row per lane) ----
+            if (p.is_logits) {
+                if (lane < n) {
+                    float *row = tb + lane * V;
+                    float m, ls;
+                    row_lse([&](int v) { return row[v]; }, V, m, ls);
+                    for (int v = 0; v < V; ++v) row[v] = logp_from(row[v], m, ls);
+                    p.rowmax[d.frame_base + t0 + lane] = m;
+                    p.rowlse[d.frame_base + t0 + lane] = ls;
+                }
+                __syncwarp();
+                if (p.logprobs) {
+                    float *lp = p.logprobs + (d.frame_base + t0) * static_cast<long long>(V);
+                    for (int i = lane; i < n * V; i += 32) lp[i] = tb[i];
+                }
+            }
+            // ---- column 0 of the trellis for rows t0 .. t0+n-1 (exclusive float64 prefix) ----
+            float2 *col0 = reinterpret_cast<float2 *>(sm + L.off_left) + b * TE;   // left[0][b][:] = {trellis[t, 0], logp[t, blank]}
             const float e0 = (lane < n) ? tb[lane * V] : 0.0f;
             if (lane < n) p.p0[d.frame_base + t0 + lane] = expf(e0);
+            float mine_f = INFINITY;
             if (t0 < infstart) {
                 xd_s[lane] = static_cast<double>(e0);
                 __syncwarp();
-                for (int i = 0; i < n; ++i) {
-                    col0_s[i] = static_cast<float>(cum);   // same value from every lane
+                double mine = 0.0;
+                for (int i = 0; i < n; ++i) {       // same chain in every lane; lane i keeps prefix i
+                    if (i == lane) mine = cum;
                     cum += xd_s[i];
                 }
-                col0_s[n] = static_cast<float>(cum);
                 __syncwarp();
+                if (t0 + lane < infstart) mine_f = static_cast<float>(mine);
             }
-            for (int i = lane; i <= n; i += 32)
-                if (t0 + i >= infstart) col0_s[i] = INFINITY;
-            __syncwarp();
-        }
-
-        // ---- phase 1: the recurrence (:372-378), 8 frames unrolled ----
-        uint32_t rowaddr = sm_base + b * tile_bytes;
-        const uint32_t rowstep = static_cast<uint32_t>(V) * 4u;
-        const uint32_t blankoff = static_cast<uint32_t>(p.blank) * 4u;
-
-        auto step = [&](int tt) {
-            const float eb = lds_f32(rowaddr + blankoff);
-            const float c0 = col0_s[tt];
-            float left = __shfl_up_sync(FULL, src, 1);
-            if (lane == 0) left = c0;
-            // chg first (it reads the *old* left neighbours), then stay / sign-difference as packed
-            // f32x2 adds (FADD2 on sm_100: one issue slot for two cells; IEEE round-to-nearest per lane)
-            float chg[K];
-#pragma unroll
-            for (int i = K - 1; i >= 0; --i) {
-                const float e = lds_f32(rowaddr + tokoff[i]);
-                chg[i] = ((i == 0) ? left : R[i - 1]) + e;    // trellis[t, j-1] + emission[t, tokens[j-1]]
-            }
-#pragma unroll
-            for (int i = 0; i + 1 < K; i += 2) {
-                const float2 st = __fadd2_rn(make_float2(R[i], R[i + 1]), make_float2(eb, eb));   // trellis[t, j] + emission[t, blank]
-                const float2 dd = __fadd2_rn(st, make_float2(-chg[i], -chg[i + 1]));             // sign set <=> chg > stay (strict)
-                R[i] = fmax_nan(st.x, chg[i]);
-                R[i + 1] = fmax_nan(st.y, chg[i + 1]);
-                acc[i] = __funnelshift_l(__float_as_uint(dd.x), acc[i], 1);
-                acc[i + 1] = __funnelshift_l(__float_as_uint(dd.y), acc[i + 1], 1);
-            }
-            if (K & 1) {
-                const float stay = R[K - 1] + eb;
-                const float dd = stay - chg[K - 1];
-                R[K - 1] = fmax_nan(stay, chg[K - 1]);
-                acc[K - 1] = __funnelshift_l(__float_as_uint(dd), acc[K - 1], 1);
-            }
-            rowaddr += rowstep;
-            ++t;
-            if (K >= 2) src = wide ? R[K - 1] : R[(K >= 2) ? K - 2 : 0];
-            else src = R[0];
-            if (src > best) { best = src; bestt = t; }
+            if (lane < n) col0[lane] = make_float2(mine_f, tb[lane * V + p.blank]);
             if (DEBUG) {
-                float *tr = p.trellis + d.trellis_off + static_cast<long long>(t) * (N + 1);
-#pragma unroll
-                for (int i = 0; i < K; ++i)
-                    if (i < ncols) tr[1 + cb + i] = R[i];
-                if (lane == 0) tr[0] = col0_s[tt + 1];
+                float *tr = p.trellis + d.trellis_off;
+                if (lane < n) tr[static_cast<long long>(t0 + lane) * (N + 1)] = mine_f;
+                if (tau == ntiles - 1 && lane == 0)
+                    tr[static_cast<long long>(T) * (N + 1)] = (T >= infstart) ? INFINITY : static_cast<float>(cum);
             }
-            if (DEBUG && p.final_col && lane == laneN) p.final_col[d.frame_base + d.seg + t] = src;
-        };
-        auto flush_if_word_done = [&]() {
-            if ((t & 31) == 0) {
-                uint32_t *w = p.bits + d.bits_off + (static_cast<long long>((t >> 5) - 1) * K) * 32 + lane;
-#pragma unroll
-                for (int i = 0; i < K; ++i) w[i * 32] = acc[i];
-            }
-        };
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8u * b);
+        }
+        while (st0 < T) scan_next();    // the tiles still in flight when the last one was issued
+        t_start = bestt;
+        best_val = best;
+    } else {
+        // ================================================================ compute warp wi
+        const int g = wi * 32 + lane;                   // global lane
+        const int r = N - 32 * W * (K - 1);             // 1..32W by construction of the (K, W) bucket
+        const bool wide = g < r;
+        const int cb = wide ? g * K : r * K + (g - r) * (K - 1);
+        const int ncols = wide ? K : K - 1;
+        const bool last_warp = (wi == W - 1);
+        // lane of this warp whose last real column is the warp's last column (K = 1: the last warp may
+        // end before lane 31); in the last warp that column is column N of the trellis
+        const int laneN = (K == 1 && last_warp) ? (N - 1 - 32 * (W - 1)) : 31;
 
-        int tt = 0;
-        for (; tt + WXB_UNROLL <= n; tt += WXB_UNROLL) {
+        uint32_t tokoff[K];
 #pragma unroll
-            for (int u = 0; u < WXB_UNROLL; ++u) step(tt + u);
-            flush_if_word_done();
+        for (int i = 0; i < K; ++i) {
+            // byte offsets (token*4) come pre-multiplied from the plan: LDS [R + UR] with a uniform row base
+            tokoff[i] = (i < ncols) ? static_cast<uint32_t>(__ldg(p.tok4 + d.tok_base + cb + i)) : 0u;
         }
-        for (; tt < n; ++tt) {
-            step(tt);
-            flush_if_word_done();
-        }
-        // this buffer is re-filled through the async proxy two tiles from now: order every lane's
-        // generic reads / in-place log-softmax writes before that copy
-        fence_proxy_async();
-        __syncwarp();
-    }
-    if (t & 31) {   // last, partial word: left-align so that frame t' sits at bit 31-(t'%32)
-        const int sh = 32 - (t & 31);
-        uint32_t *w = p.bits + d.bits_off + (static_cast<long long>(t >> 5) * K) * 32 + lane;
+        float R[K];
+        uint32_t acc[K];
 #pragma unroll
-        for (int i = 0; i < K; ++i) w[i * 32] = acc[i] << sh;
+        for (int i = 0; i < K; ++i) { R[i] = -INFINITY; acc[i] = 0u; }   // trellis[0, 1:] = -inf  (:369)
+        float src = -INFINITY;          // this lane's last real column at the current row
+        const uint32_t rowstep = static_cast<uint32_t>(V) * 4u;
+        const uint32_t left_in0 = sm_base + L.off_left + wi * left_stride_w;      // left[wi][b][tt]
+        const uint32_t wait_bar0 = (wi == 0) ? bar_full : bar_edge + 8u * NB * wi;
+        const uint32_t next_bar0 = last_warp ? bar_empty : bar_edge + 8u * NB * (wi + 1);
+        uint32_t *bits_w = p.bits + d.bits_off + (static_cast<long long>(wi) * K) * 32 + lane;   // next word to flush
+        const int bits_step = W * K * 32;                                          // words per 32 frames
+
+        int t = 0;                      // frames consumed so far == current trellis row
+        int b = -1;                     // ring position and lap parity of the current tile
+        uint32_t ph = 0;
+        for (int tau = 0; tau < ntiles; ++tau) {
+            // branch-free ring step: a select keeps b / ph (and every address derived from them) in
+            // uniform registers, an `if` does not
+            ++b;
+            const bool wrap = (b == NB);
+            b = wrap ? 0 : b;
+            ph ^= wrap ? 1u : 0u;
+            const int n = min(TE, T - tau * TE);
+            mbar_wait(wait_bar0 + 8u * b, ph);
+
+            uint32_t rowaddr = sm_base + b * L.tile_bytes;
+            uint32_t left_in = left_in0 + static_cast<uint32_t>(b * TE) * 8u;     // + 8*tt as the tile advances
+            uint32_t left_out = left_in + left_stride_w;
+            asm volatile("" : "+r"(left_in), "+r"(left_out));   // materialise once per tile, not per frame under a predicate
+
+            // ---- the recurrence (:372-378) ----
+            auto step = [&](int u) {         // u = frame inside the current unrolled block (a literal after unrolling)
+                const float2 lv = lds_f32x2(left_in + 8u * u);        // {trellis[t, my first column - 1], logp[t, blank]}
+                const float eb = lv.y;
+                float left = __shfl_up_sync(FULL, src, 1);
+                if (lane == 0) left = lv.x;
+                if (lane == laneN) sts_f32x2(left_out + 8u * u, src, eb);   // row t of my last column -> warp wi+1
+                // chg first (it reads the *old* left neighbours), then stay / sign-difference as packed
+                // f32x2 adds (FADD2 on sm_100: one issue slot for two cells; IEEE round-to-nearest per lane)
+                float chg[K];
+#pragma unroll
+                for (int i = K - 1; i >= 0; --i) {
+                    const float e = lds_f32(rowaddr + tokoff[i]);
+                    chg[i] = ((i == 0) ? left : R[i - 1]) + e;    // trellis[t, j-1] + emission[t, tokens[j-1]]
+                }
+#pragma unroll
+                for (int i = 0; i + 1 < K; i += 2) {
+                    const float2 st = __fadd2_rn(make_float2(R[i], R[i + 1]), make_float2(eb, eb));   // trellis[t, j] + emission[t, blank]
+                    const float2 dd = __fadd2_rn(st, make_float2(-chg[i], -chg[i + 1]));             // sign set <=> chg > stay (strict)
+                    R[i] = fmax_nan(st.x, chg[i]);
+                    R[i + 1] = fmax_nan(st.y, chg[i + 1]);
+                    acc[i] = __funnelshift_l(__float_as_uint(dd.x), acc[i], 1);
+                    acc[i + 1] = __funnelshift_l(__float_as_uint(dd.y), acc[i + 1], 1);
+                }
+                if (K & 1) {
+                    const float stay = R[K - 1] + eb;
+                    const float dd = stay - chg[K - 1];
+                    R[K - 1] = fmax_nan(stay, chg[K - 1]);
+                    acc[K - 1] = __funnelshift_l(__float_as_uint(dd), acc[K - 1], 1);
+                }
+                rowaddr += rowstep;
+                ++t;
+                if (K >= 2) src = wide ? R[K - 1] : R[(K >= 2) ? K - 2 : 0];
+                else src = R[0];
+                if (DEBUG) {
+                    float *tr = p.trellis + d.trellis_off + static_cast<long long>(t) * (N + 1);
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                        if (i < ncols) tr[1 + cb + i] = R[i];
+                    if (p.final_col && last_warp && lane == laneN) p.final_col[d.frame_base + d.seg + t] = src;
+                }
+            };
+            auto flush_if_word_done = [&]() {
+                if ((t & 31) == 0) {
+#pragma unroll
+                    for (int i = 0; i < K; ++i) bits_w[i * 32] = acc[i];
+                    bits_w += bits_step;
+                }
+            };
+
+            int tt = 0;
+            for (; tt + WXB_UNROLL <= n; tt += WXB_UNROLL) {
+#pragma unroll
+                for (int u = 0; u < WXB_UNROLL; ++u) step(u);
+                left_in += 8u * WXB_UNROLL;
+                left_out += 8u * WXB_UNROLL;
+                flush_if_word_done();
+            }
+            for (; tt < n; ++tt) {
+                step(0);
+                left_in += 8u;
+                left_out += 8u;
+                flush_if_word_done();
+            }
+            __syncwarp();
+            // hand the tile on: boundary values to warp wi+1, or the buffer back to the producer
+            if (lane == 0) mbar_arrive(next_bar0 + 8u * b);
+        }
+        if (t & 31) {   // last, partial word: left-align so that frame t' sits at bit 31-(t'%32)
+            const int sh = 32 - (t & 31);
+#pragma unroll
+            for (int i = 0; i < K; ++i) bits_w[i * 32] = acc[i] << sh;
+        }
+        if (last_warp && lane == laneN) *reinterpret_cast<float *>(sm + L.off_fin) = src;      // trellis[T, N]
     }
-    __threadfence_block();
-    __syncwarp();
+    __syncthreads();      // every warp's choice words (and trellis[T, N]) are visible to the walker
+    if (wi != W) return;  // the producer warp holds the arg-max and walks back
+    // best_val covers rows 0..T-1; row T wins only if strictly larger (first maximal index)
+    if (T > 0 && *reinterpret_cast<const float *>(sm + L.off_fin) > best_val) t_start = T;
     if (p.trace && lane == 0) p.trace[4ll * (seg_first + blockIdx.x) + 1] = global_ns();
 
-    // ---- phase 2: backtrack (:395-421) over the choice bits; control flow is warp-uniform ----
+    // ---- backtrack (:395-421) over the choice bits; control flow is warp-uniform ----
     // The walk needs one choice word per visited (column, 32-frame word) pair: ~N + T/32
-    // *dependent* loads if done naively (measured: 30% of all warp time).  Instead the warp
-    // fetches a window of 32 columns x 4 words (128 frames) with 4 independent loads per lane
-    // and walks inside it on register shuffles; a new window is fetched only when the path leaves
-    // the block: about max(N/32, T/128) dependent round trips per segment.
-    const int t_start = __shfl_sync(FULL, bestt, laneN);
+    // *dependent* loads if done naively.  Instead the warp fetches a window of 32 columns x 4 words
+    // (128 frames) with 4 independent loads per lane and walks inside it on register shuffles; a new
+    // window is fetched only when the path leaves the block: about max(N/32, T/128) dependent round
+    // trips per segment.
+    // (the descriptor is read again rather than kept live across the recurrence: registers there are
+    // worth more than one L2 hit here)
+    const SegDesc db = p.segs[seg_first + blockIdx.x];
+    const int r = db.N - 32 * W * (K - 1);
+    const long long wstep = static_cast<long long>(W) * K * 32;
     int status = 0;
-    int *cstart = p.c_start + d.tok_base;
+    int *cstart = p.c_start + db.tok_base;
     if (t_start == 0) {
         status = 1;                                  // empty walk -> for/else -> None
     } else {
-        int j = N;
+        int j = db.N;
         int s = t_start - 1;                         // frame of the current point
         bool done = false;
         while (!done) {
@@ -352,13 +478,13 @@ __global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg
             uint32_t wA = 0u, wB = 0u, wC = 0u, wD = 0u;
             const int c = j0 - lane;
             if (c >= 1) {
-                int ln, slot;
-                owner_of<K>(c - 1, r, ln, slot);
-                const uint32_t *bp = p.bits + d.bits_off + (static_cast<long long>(w0) * K + slot) * 32 + ln;
+                int g, slot;
+                owner_of<K>(c - 1, r, g, slot);
+                const uint32_t *bp = p.bits + db.bits_off + static_cast<long long>(w0) * wstep + ((g >> 5) * K + slot) * 32 + (g & 31);
                 wA = __ldcg(bp);
-                if (w0 >= 1) wB = __ldcg(bp - 1 * K * 32);
-                if (w0 >= 2) wC = __ldcg(bp - 2 * K * 32);
-                if (w0 >= 3) wD = __ldcg(bp - 3 * K * 32);
+                if (w0 >= 1) wB = __ldcg(bp - 1 * wstep);
+                if (w0 >= 2) wC = __ldcg(bp - 2 * wstep);
+                if (w0 >= 3) wD = __ldcg(bp - 3 * wstep);
             }
             while (true) {
                 const int dw = w0 - (s >> 5);        // 0..3 inside the window
@@ -382,11 +508,11 @@ __global__ void __launch_bounds__(32) align_kernel(const Params p, const int seg
         }
     }
     if (lane == 0) {
-        p.status[d.seg] = status;
-        p.nframes[d.seg] = status ? 0 : t_start;
+        p.status[db.seg] = status;
+        p.nframes[db.seg] = status ? 0 : t_start;
         if (p.trace) p.trace[4ll * (seg_first + blockIdx.x) + 2] = global_ns();
     }
-    // phase 3 (merge_repeats, scores, timestamps) runs token-parallel in finalize_kernel
+    // merge_repeats, scores and timestamps run token-parallel in finalize_kernel
 }
 
 struct FinBlock { int desc; int k0; };   // finalize_kernel work item (see wxb_align.cu)
