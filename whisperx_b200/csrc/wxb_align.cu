@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const Params p, const Fin
     const float *Eg = p.emis + d.emis_off;
     const int sf = p.c_start[o];
     const int ef = (k == N - 1) ? t_start : p.c_start[o + 1];
-    const int tk = __ldg(p.tokens + o);
+    const int tk = __ldg(p.tok4 + o) >> 2;
     float x = __ldg(Eg + static_cast<size_t>(sf) * V + tk);
     if (p.is_logits) x = logp_from(x, p.rowmax[d.frame_base + sf], p.rowlse[d.frame_base + sf]);
     double sum = static_cast<double>(expf(x));           // Python sum(): 0 + p_first + ...
@@ -260,20 +260,53 @@ struct DevBuf {
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
+// One device allocation mirrored by one pinned host buffer: a plan's metadata is assembled in the
+// mirror and goes up in a single cudaMemcpyAsync.  Arenas are pooled per context (grow-only).
+struct Arena {
+    unsigned char *dev = nullptr, *host = nullptr;
+    size_t cap = 0;
+    cudaEvent_t uploaded = nullptr;
+    cudaError_t ensure(size_t bytes) {
+        if (!uploaded) {
+            cudaError_t e = cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        if (bytes <= cap) return cudaSuccess;
+        release_mem();
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dev), want);
+        if (e != cudaSuccess) { dev = nullptr; return e; }
+        e = cudaHostAlloc(reinterpret_cast<void **>(&host), want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { cudaFree(dev); dev = nullptr; host = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release_mem() {
+        if (dev) cudaFree(dev);
+        if (host) cudaFreeHost(host);
+        dev = host = nullptr; cap = 0;
+    }
+    void release() { release_mem(); if (uploaded) cudaEventDestroy(uploaded); uploaded = nullptr; }
+};
+
 struct wxb_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t main = nullptr;              // used by wxb_align_host
+    cudaStream_t main = nullptr;              // used by wxb_align_host and for plan uploads
+    cudaStream_t copy = nullptr;              // host->device emission chunks (wxb_align_host)
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;        // one per emission chunk in flight
     DevBuf bits, p0, rowmax, rowlse, nframes_scratch, trace;
     int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
     bool want_trace = false;                  // WXB_TRACE=1
+    size_t chunk_bytes = 128u << 20;          // WXB_CHUNK_MB: emission bytes per pipelined H2D chunk
+    std::vector<Arena *> arena_pool;          // metadata arenas of destroyed plans, ready for reuse
     // wxb_align_host staging
     DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
 };
 
-struct Bucket { int K; int W; int NB; size_t smem; int first; int count; long long cost; int maxT; };
+struct Bucket { int K; int W; int NB; size_t smem; int first; int count; long long cost; int maxT; int chunk; };
 
 struct wxb_plan {
     wxb_ctx *ctx = nullptr;
@@ -281,23 +314,24 @@ struct wxb_plan {
     int V = 0, blank = 0, TE = 32;
     uint32_t flags = 0;
     bool has_sec = false, has_words = false, has_round_np = false;
-    std::vector<Bucket> buckets;
+    std::vector<Bucket> buckets;              // chunk-major, longest segments first inside a chunk
+    std::vector<int64_t> chunk_row;           // [n_chunks+1] emission row range of each chunk
     int n_short = 0;
     long long bits_words = 0, trellis_floats = 0, cells = 0, alg_bytes = 0;
     int n_fin_blocks = 0, n_desc = 0;
     std::vector<SegDesc> host_descs;          // kept for wxb_plan_debug_trace
-    DevBuf d_fin;
-    DevBuf d_round_np;
-    DevBuf d_segs, d_tokens, d_tok4, d_t1, d_ratio, d_short, d_word_seg, d_seg_tok_base, d_wchar_off, d_wchar_idx;
-    ~wxb_plan() {
-        DevBuf *all[] = {&d_round_np, &d_fin, &d_segs, &d_tokens, &d_tok4, &d_t1, &d_ratio, &d_short, &d_word_seg, &d_seg_tok_base, &d_wchar_off, &d_wchar_idx};
-        for (DevBuf *b : all) b->release();
-    }
+    Arena *arena = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool ran = false;
+    // device views into the arena
+    SegDesc *d_segs = nullptr; FinBlock *d_fin = nullptr; int *d_tok4 = nullptr; ShortSeg *d_short = nullptr;
+    double *d_t1 = nullptr, *d_ratio = nullptr; unsigned char *d_round_np = nullptr;
+    int *d_word_seg = nullptr; long long *d_seg_tok_base = nullptr, *d_wchar_off = nullptr; int *d_wchar_idx = nullptr;
 };
 
 // Warps and tokens-per-lane for a transcript of n tokens: as few compute warps as keep K <= k_target
 // (more columns per lane amortise the per-frame overhead; more warps shorten the segment's latency).
-static int g_k_target = 6;
+static int g_k_target = 5;
 
 static bool shape_of(long long n, int *W, int *K) {
     if (n <= 0) return false;
@@ -318,9 +352,12 @@ static int tokens_per_lane(long long n) {
 
 // Frames per shared-memory tile (cp.async.bulk needs 16-byte multiples, i.e. TE % 4 == 0): 32 when the
 // widest CTA of the batch still fits a ring of at least 2 tiles, else 16, 8, 4.
+static int g_tile_pref = 32;     // WXB_TILE_FRAMES (experiments): largest tile length tried
+
 static int pick_tile(int V, int Wmax, int *TE) {
     const int pref[4] = {32, 16, 8, 4};
     for (int i = 0; i < 4; ++i) {
+        if (pref[i] > g_tile_pref) continue;
         if (smem_layout(Wmax, 2, pref[i], V).total <= static_cast<uint32_t>(SMEM_LIMIT)) { *TE = pref[i]; return 0; }
     }
     return -1;
@@ -372,8 +409,11 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     if (const char *e = getenv("WXB_SIDE_STREAMS")) c->side_streams = std::max(1, std::min(NSIDE, atoi(e)));
     if (const char *e = getenv("WXB_TRACE")) c->want_trace = atoi(e) != 0;
     if (const char *e = getenv("WXB_K_TARGET")) g_k_target = std::max(1, std::min(KMAX, atoi(e)));
+    if (const char *e = getenv("WXB_TILE_FRAMES")) g_tile_pref = std::max(4, std::min(32, atoi(e)));
+    if (const char *e = getenv("WXB_CHUNK_MB")) c->chunk_bytes = static_cast<size_t>(std::max(1, atoi(e))) << 20;
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
     for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
@@ -390,12 +430,16 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
 extern "C" void wxb_destroy(wxb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
     DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->nframes_scratch, &c->h_emis, &c->h_path_tok};
     for (DevBuf *b : bufs) b->release();
     for (auto &b : c->h_i32) b.release();
     for (auto &b : c->h_f64) b.release();
     for (auto &b : c->h_f32) b.release();
+    for (Arena *a : c->arena_pool) { a->release(); delete a; }
+    for (cudaEvent_t ev : c->ev_chunk) cudaEventDestroy(ev);
     if (c->main) cudaStreamDestroy(c->main);
+    if (c->copy) cudaStreamDestroy(c->copy);
     for (int i = 0; i < NSIDE; ++i) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
@@ -418,15 +462,18 @@ extern "C" int wxb_get_limits(const wxb_ctx *ctx, wxb_limits *out) {
 }
 
 // ------------------------------------------------------------------ ABI: plan
-template <class T>
-static cudaError_t upload(DevBuf &b, const T *src, size_t n) {
-    cudaError_t e = b.ensure(std::max<size_t>(n, 1) * sizeof(T));
-    if (e != cudaSuccess) return e;
-    if (n == 0) return cudaSuccess;
-    return cudaMemcpy(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice);
+static size_t up256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+static void plan_free(wxb_plan *pl) {
+    if (!pl) return;
+    if (pl->arena) pl->ctx->arena_pool.push_back(pl->arena);
+    delete pl;
 }
 
-extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out) {
+// chunk_rows = 0: one chunk (the emissions are already resident).  Otherwise the emission matrix
+// arrives in chunks of chunk_rows rows (wxb_align_host starts those copies before planning) and a
+// segment belongs to the chunk that holds its last row: its kernels wait for that chunk only.
+static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_rows, wxb_plan **out) {
     if (!ctx || !bt || !out) return fail(WXB_EINVAL, "wxb_plan_create: NULL argument");
     *out = nullptr;
     const int64_t S = bt->n_segments;
@@ -441,7 +488,7 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
 
     wxb_plan *pl = new (std::nothrow) wxb_plan();
     if (!pl) return fail(WXB_ENOMEM, "wxb_plan_create: out of host memory");
-    struct Guard { wxb_plan *p; ~Guard() { delete p; } } guard{pl};
+    struct Guard { wxb_plan *p; ~Guard() { plan_free(p); } } guard{pl};
     pl->ctx = ctx;
     pl->S = S;
     pl->V = bt->vocab;
@@ -464,21 +511,33 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
     pl->sum_T = fo[S];
     pl->sum_N = to[S];
     if (pl->sum_N > 0 && !bt->tokens) return fail(WXB_EINVAL, "wxb_plan_create: tokens is NULL");
-    for (int64_t i = to[0]; i < to[S]; ++i)
-        if (bt->tokens[i] < 0 || bt->tokens[i] >= pl->V) return fail(WXB_EINVAL, "wxb_plan_create: tokens[%lld]=%d outside [0,%d)", (long long)i, bt->tokens[i], pl->V);
+    const int64_t W = pl->W;
+    if (pl->has_words) {
+        if (bt->word_off[0] != 0 || bt->word_off[S] != W) return fail(WXB_EINVAL, "wxb_plan_create: word_off must run from 0 to n_words");
+        for (int64_t s = 0; s < S; ++s)
+            if (bt->word_off[s + 1] < bt->word_off[s]) return fail(WXB_EINVAL, "wxb_plan_create: word_off not ascending");
+        for (int64_t w = 0; w < W; ++w)
+            if (bt->wchar_off[w + 1] < bt->wchar_off[w]) return fail(WXB_EINVAL, "wxb_plan_create: wchar_off not ascending");
+    }
 
-    // ---- bucket by tokens-per-lane, shortcut provably failing segments ----
+    // ---- shape every segment; shortcut the provably failing ones ----
     std::vector<SegDesc> descs;
     descs.reserve(static_cast<size_t>(S));
+    std::vector<int> desc_chunk;
+    desc_chunk.reserve(static_cast<size_t>(S));
     std::vector<ShortSeg> shorts;
-    std::vector<long long> seg_tok_base(static_cast<size_t>(S));
     long long trellis_off = 0;
     int wmax = 1;
     const bool no_shortcut = (bt->flags & WXB_F_NO_SHORTCUT) != 0;
+    pl->chunk_row.push_back(0);
+    if (chunk_rows > 0)
+        for (int64_t r = chunk_rows; r < fo[S]; r += chunk_rows) pl->chunk_row.push_back(r);
+    pl->chunk_row.push_back(fo[S]);
+    const int n_chunks = static_cast<int>(pl->chunk_row.size()) - 1;
     for (int64_t s = 0; s < S; ++s) {
         const int T = bt->frame_len ? bt->frame_len[s] : static_cast<int>(fo[s + 1] - fo[s]);
         const int N = static_cast<int>(to[s + 1] - to[s]);
-        seg_tok_base[s] = to[s];
+        const int chunk = chunk_rows > 0 ? static_cast<int>(std::min<int64_t>((fo[s] + std::max(T, 1) - 1) / chunk_rows, n_chunks - 1)) : 0;
         const long long this_trellis = trellis_off;
         trellis_off += static_cast<long long>(T + 1) * (N + 1);
         int K = -1, Wc = 0;
@@ -495,7 +554,7 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
         d.tok_base = to[s];
         d.bits_off = 0;
         d.trellis_off = this_trellis;
-        d.T = T; d.N = N; d.seg = static_cast<int>(s); d.K = K; d.W = Wc; d.pad = 0;
+        d.T = T; d.N = N; d.seg = static_cast<int>(s); d.K = K; d.W = Wc; d.pad = chunk;
         wmax = std::max(wmax, Wc);
         descs.push_back(d);
         pl->cells += static_cast<long long>(T) * N;
@@ -505,9 +564,10 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
     pl->n_short = static_cast<int>(shorts.size());
     if (pick_tile(pl->V, wmax, &pl->TE) != 0)
         return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory for a %d-warp segment", pl->V, SMEM_LIMIT, wmax);
-    // one launch per (warps, tokens-per-lane) class; longest-first inside a class: the block
+    // one launch per (chunk, warps, tokens-per-lane) class; longest-first inside a class: the block
     // scheduler hands out CTAs in index order (LPT)
     std::stable_sort(descs.begin(), descs.end(), [](const SegDesc &a, const SegDesc &b) {
+        if (a.pad != b.pad) return a.pad < b.pad;
         if (a.W != b.W) return a.W > b.W;
         if (a.K != b.K) return a.K > b.K;
         return a.T > b.T;
@@ -516,8 +576,8 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
     for (size_t i = 0; i < descs.size(); ++i) {
         descs[i].bits_off = bits;
         bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].W * descs[i].K * 32;
-        if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W) {
-            Bucket b{descs[i].K, descs[i].W, 0, 0, static_cast<int>(i), 0, 0, descs[i].T};
+        if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W || descs[i].pad != descs[i - 1].pad) {
+            Bucket b{descs[i].K, descs[i].W, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad};
             b.NB = pick_ring(b.W, pl->TE, pl->V, &b.smem);
             pl->buckets.push_back(b);
         }
@@ -525,61 +585,115 @@ extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out
         pl->buckets.back().cost += static_cast<long long>(descs[i].T) * descs[i].K * descs[i].W;
     }
     pl->bits_words = bits;
-    std::vector<FinBlock> fin;
-    for (size_t i = 0; i < descs.size(); ++i)
-        for (int k0 = 0; k0 < descs[i].N; k0 += 128) fin.push_back({static_cast<int>(i), k0});
-    pl->n_fin_blocks = static_cast<int>(fin.size());
-    pl->n_desc = static_cast<int>(descs.size());
-    pl->host_descs = descs;
-    // launch order = placement priority: classes holding the longest segments go first (LPT across
-    // classes; a segment's latency grows with its frame count, not with its class's total cost)
+    // launch order = placement priority: inside a chunk, classes holding the longest segments go
+    // first (LPT across classes; a segment's latency grows with its frame count)
     std::stable_sort(pl->buckets.begin(), pl->buckets.end(), [](const Bucket &a, const Bucket &b) {
+        if (a.chunk != b.chunk) return a.chunk < b.chunk;
         if (a.maxT != b.maxT) return a.maxT > b.maxT;
         return a.cost > b.cost;
     });
+    size_t n_fin = 0;
+    for (const SegDesc &d : descs) n_fin += static_cast<size_t>((d.N + 127) / 128);
+    pl->n_fin_blocks = static_cast<int>(n_fin);
+    pl->n_desc = static_cast<int>(descs.size());
+    if (ctx->want_trace) pl->host_descs = descs;
 
-    // ---- upload ----
-    std::vector<int> tok4(static_cast<size_t>(std::max<int64_t>(pl->sum_N, 1)));
-    for (int64_t i = 0; i < pl->sum_N; ++i) tok4[i] = bt->tokens[i] * 4;
-    CUDA_TRY(upload(pl->d_segs, descs.data(), descs.size()));
-    CUDA_TRY(upload(pl->d_fin, fin.data(), fin.size()));
-    CUDA_TRY(upload(pl->d_tokens, bt->tokens, static_cast<size_t>(pl->sum_N)));
-    CUDA_TRY(upload(pl->d_tok4, tok4.data(), static_cast<size_t>(pl->sum_N)));
-    CUDA_TRY(upload(pl->d_short, shorts.data(), shorts.size()));
-    if (pl->has_sec) {
-        CUDA_TRY(upload(pl->d_t1, bt->seg_t1, static_cast<size_t>(S)));
-        CUDA_TRY(upload(pl->d_ratio, bt->seg_ratio, static_cast<size_t>(S)));
-        if (bt->seg_round_np) CUDA_TRY(upload(pl->d_round_np, bt->seg_round_np, static_cast<size_t>(S)));
-    }
+    // ---- one arena: lay out, fill the pinned mirror, upload once ----
+    const size_t sN = static_cast<size_t>(pl->sum_N), nW = static_cast<size_t>(W);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += up256(std::max<size_t>(bytes, 1)); return o; };
+    const size_t o_segs = take(descs.size() * sizeof(SegDesc));
+    const size_t o_fin = take(n_fin * sizeof(FinBlock));
+    const size_t o_tok4 = take(sN * 4);
+    const size_t o_short = take(shorts.size() * sizeof(ShortSeg));
+    const size_t o_t1 = take(pl->has_sec ? static_cast<size_t>(S) * 8 : 0);
+    const size_t o_ratio = take(pl->has_sec ? static_cast<size_t>(S) * 8 : 0);
     pl->has_round_np = pl->has_sec && bt->seg_round_np != nullptr;
-    if (pl->has_words) {
-        const int64_t W = pl->W;
-        if (bt->word_off[0] != 0 || bt->word_off[S] != W) return fail(WXB_EINVAL, "wxb_plan_create: word_off must run from 0 to n_words");
-        std::vector<int> word_seg(static_cast<size_t>(W));
-        for (int64_t s = 0; s < S; ++s) {
-            if (bt->word_off[s + 1] < bt->word_off[s]) return fail(WXB_EINVAL, "wxb_plan_create: word_off not ascending");
-            for (int64_t w = bt->word_off[s]; w < bt->word_off[s + 1]; ++w) word_seg[w] = static_cast<int>(s);
-        }
-        for (int64_t w = 0; w < W; ++w) {
-            if (bt->wchar_off[w + 1] < bt->wchar_off[w]) return fail(WXB_EINVAL, "wxb_plan_create: wchar_off not ascending");
-            const int N = static_cast<int>(to[word_seg[w] + 1] - to[word_seg[w]]);
-            for (int64_t i = bt->wchar_off[w]; i < bt->wchar_off[w + 1]; ++i)
-                if (bt->wchar_idx[i] < -1 || bt->wchar_idx[i] >= N) return fail(WXB_EINVAL, "wxb_plan_create: wchar_idx[%lld]=%d outside [-1,%d)", (long long)i, bt->wchar_idx[i], N);
-        }
-        CUDA_TRY(upload(pl->d_word_seg, word_seg.data(), word_seg.size()));
-        CUDA_TRY(upload(pl->d_seg_tok_base, seg_tok_base.data(), seg_tok_base.size()));
-        CUDA_TRY(upload(pl->d_wchar_off, bt->wchar_off, static_cast<size_t>(W + 1)));
-        CUDA_TRY(upload(pl->d_wchar_idx, bt->wchar_idx, static_cast<size_t>(bt->wchar_off[W])));
+    const size_t o_rnp = take(pl->has_round_np ? static_cast<size_t>(S) : 0);
+    const size_t o_wseg = take(pl->has_words ? nW * 4 : 0);
+    const size_t o_stb = take(pl->has_words ? static_cast<size_t>(S) * 8 : 0);
+    const size_t o_woff = take(pl->has_words ? (nW + 1) * 8 : 0);
+    const size_t n_wc = pl->has_words ? static_cast<size_t>(bt->wchar_off[W]) : 0;
+    const size_t o_widx = take(n_wc * 4);
+
+    Arena *ar = nullptr;
+    if (!ctx->arena_pool.empty()) { ar = ctx->arena_pool.back(); ctx->arena_pool.pop_back(); }
+    else ar = new (std::nothrow) Arena();
+    if (!ar) return fail(WXB_ENOMEM, "wxb_plan_create: out of host memory");
+    pl->arena = ar;
+    CUDA_TRY(ar->ensure(off));
+    unsigned char *h = ar->host;
+    memcpy(h + o_segs, descs.data(), descs.size() * sizeof(SegDesc));
+    {
+        FinBlock *fin = reinterpret_cast<FinBlock *>(h + o_fin);
+        size_t k = 0;
+        for (size_t i = 0; i < descs.size(); ++i)
+            for (int k0 = 0; k0 < descs[i].N; k0 += 128) fin[k++] = {static_cast<int>(i), k0};
     }
+    {
+        int *tok4 = reinterpret_cast<int *>(h + o_tok4);
+        const int32_t *tk = bt->tokens;
+        const uint32_t V = static_cast<uint32_t>(pl->V);
+        uint32_t bad = 0;
+        for (size_t i = 0; i < sN; ++i) {
+            bad |= (static_cast<uint32_t>(tk[i]) >= V);       // negative ids wrap to large unsigned values
+            tok4[i] = tk[i] * 4;
+        }
+        if (bad)
+            for (size_t i = 0; i < sN; ++i)
+                if (tk[i] < 0 || tk[i] >= pl->V) return fail(WXB_EINVAL, "wxb_plan_create: tokens[%lld]=%d outside [0,%d)", (long long)i, tk[i], pl->V);
+    }
+    if (!shorts.empty()) memcpy(h + o_short, shorts.data(), shorts.size() * sizeof(ShortSeg));
+    if (pl->has_sec) {
+        memcpy(h + o_t1, bt->seg_t1, static_cast<size_t>(S) * 8);
+        memcpy(h + o_ratio, bt->seg_ratio, static_cast<size_t>(S) * 8);
+        if (pl->has_round_np) memcpy(h + o_rnp, bt->seg_round_np, static_cast<size_t>(S));
+    }
+    if (pl->has_words) {
+        int *word_seg = reinterpret_cast<int *>(h + o_wseg);
+        long long *stb = reinterpret_cast<long long *>(h + o_stb);
+        for (int64_t s = 0; s < S; ++s) {
+            stb[s] = to[s];
+            const int N = static_cast<int>(to[s + 1] - to[s]);
+            for (int64_t w = bt->word_off[s]; w < bt->word_off[s + 1]; ++w) {
+                word_seg[w] = static_cast<int>(s);
+                for (int64_t i = bt->wchar_off[w]; i < bt->wchar_off[w + 1]; ++i)
+                    if (bt->wchar_idx[i] < -1 || bt->wchar_idx[i] >= N) return fail(WXB_EINVAL, "wxb_plan_create: wchar_idx[%lld]=%d outside [-1,%d)", (long long)i, bt->wchar_idx[i], N);
+            }
+        }
+        memcpy(h + o_woff, bt->wchar_off, (nW + 1) * 8);
+        if (n_wc) memcpy(h + o_widx, bt->wchar_idx, n_wc * 4);
+    }
+    CUDA_TRY(cudaMemcpyAsync(ar->dev, ar->host, off, cudaMemcpyHostToDevice, ctx->main));
+    CUDA_TRY(cudaEventRecord(ar->uploaded, ctx->main));
+    unsigned char *dv = ar->dev;
+    pl->d_segs = reinterpret_cast<SegDesc *>(dv + o_segs);
+    pl->d_fin = reinterpret_cast<FinBlock *>(dv + o_fin);
+    pl->d_tok4 = reinterpret_cast<int *>(dv + o_tok4);
+    pl->d_short = reinterpret_cast<ShortSeg *>(dv + o_short);
+    pl->d_t1 = reinterpret_cast<double *>(dv + o_t1);
+    pl->d_ratio = reinterpret_cast<double *>(dv + o_ratio);
+    pl->d_round_np = dv + o_rnp;
+    pl->d_word_seg = reinterpret_cast<int *>(dv + o_wseg);
+    pl->d_seg_tok_base = reinterpret_cast<long long *>(dv + o_stb);
+    pl->d_wchar_off = reinterpret_cast<long long *>(dv + o_woff);
+    pl->d_wchar_idx = reinterpret_cast<int *>(dv + o_widx);
     guard.p = nullptr;
     *out = pl;
     return WXB_OK;
 }
 
+extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out) {
+    return plan_create_impl(ctx, bt, 0, out);
+}
+
 extern "C" void wxb_plan_destroy(wxb_plan *plan) {
     if (!plan) return;
     cudaSetDevice(plan->ctx->device);
-    delete plan;
+    // the arena goes back to the pool: nothing may still be reading it
+    if (plan->arena && plan->arena->uploaded) cudaEventSynchronize(plan->arena->uploaded);
+    if (plan->ran) cudaStreamSynchronize(plan->last_stream);
+    plan_free(plan);
 }
 
 extern "C" int wxb_plan_launch_count(const wxb_plan *plan) {
@@ -596,7 +710,11 @@ extern "C" int wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg
 }
 
 // ------------------------------------------------------------------ ABI: run
-extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *o, void *stream_, float *elapsed_dp_ms) {
+// chunk_ready != nullptr: pipelined host path — chunk c of the emissions is on its way to `emis`
+// on the copy stream and chunk_ready[c] fires when it has landed; the kernels of a segment wait
+// for the chunk that holds its last row.
+static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_ready, const wxb_outputs *o, cudaStream_t st,
+                    float *elapsed_dp_ms) {
     if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
     if (pl->S == 0) { if (elapsed_dp_ms) *elapsed_dp_ms = 0.f; return WXB_OK; }
     if (!o->status || !o->char_start || !o->char_end || !o->char_score)
@@ -615,7 +733,6 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
 
     wxb_ctx *c = pl->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream_);
     CUDA_TRY(c->bits.ensure(static_cast<size_t>(std::max<long long>(pl->bits_words, 1)) * 4));
     CUDA_TRY(c->p0.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
     if (logits) {
@@ -631,9 +748,8 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     Params P;
     memset(&P, 0, sizeof P);
     P.emis = emis;
-    P.tokens = pl->d_tokens.as<int>();
-    P.tok4 = pl->d_tok4.as<int>();
-    P.segs = pl->d_segs.as<SegDesc>();
+    P.tok4 = pl->d_tok4;
+    P.segs = pl->d_segs;
     P.bits = c->bits.as<uint32_t>();
     P.p0 = c->p0.as<float>();
     P.rowmax = c->rowmax.as<float>();
@@ -643,8 +759,8 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     P.c_start = o->char_start; P.c_end = o->char_end; P.c_score = o->char_score;
     if (want_sec) {
         P.c_start_s = o->char_start_s; P.c_end_s = o->char_end_s; P.c_score_r = o->char_score_r;
-        P.seg_t1 = pl->d_t1.as<double>(); P.seg_ratio = pl->d_ratio.as<double>();
-        P.seg_round_np = pl->has_round_np ? pl->d_round_np.as<unsigned char>() : nullptr;
+        P.seg_t1 = pl->d_t1; P.seg_ratio = pl->d_ratio;
+        P.seg_round_np = pl->has_round_np ? pl->d_round_np : nullptr;
     }
     P.path_tok = o->path_token; P.path_logp = o->path_logp;
     P.final_col = o->final_col; P.trellis = o->trellis; P.logprobs = o->logprobs;
@@ -653,19 +769,29 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
         P.trace = c->trace.as<unsigned long long>();
     }
 
+    pl->last_stream = st;
+    pl->ran = true;
+    CUDA_TRY(cudaStreamWaitEvent(st, pl->arena->uploaded, 0));     // the plan's metadata upload (ctx stream)
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t0, st));
     const int nb = static_cast<int>(pl->buckets.size());
-    if (nb == 1) {
+    if (nb == 1 && !chunk_ready) {
         const Bucket &b = pl->buckets[0];
         CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, st, debug));
-    } else if (nb > 1) {
-        // buckets are independent: fork onto side streams so that every SM sees a mix of K classes
+    } else if (nb >= 1) {
+        // classes are independent: fork onto side streams so that every SM sees a mix of them
         const int used = std::min(nb, c->side_streams);
         CUDA_TRY(cudaEventRecord(c->ev_fork, st));
         for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+        int seen_chunk[NSIDE];
+        for (int i = 0; i < NSIDE; ++i) seen_chunk[i] = -1;
         for (int i = 0; i < nb; ++i) {
             const Bucket &b = pl->buckets[i];
-            CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, c->side[i % used], debug));
+            const int si = i % used;
+            if (chunk_ready && seen_chunk[si] < b.chunk) {
+                CUDA_TRY(cudaStreamWaitEvent(c->side[si], chunk_ready[b.chunk], 0));
+                seen_chunk[si] = b.chunk;
+            }
+            CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, c->side[si], debug));
         }
         for (int i = 0; i < used; ++i) {
             CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));
@@ -674,11 +800,11 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     }
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t1, st));
     if (pl->n_fin_blocks > 0) {
-        finalize_kernel<<<pl->n_fin_blocks, 128, 0, st>>>(P, pl->d_fin.as<FinBlock>());
+        finalize_kernel<<<pl->n_fin_blocks, 128, 0, st>>>(P, pl->d_fin);
         CUDA_TRY(cudaGetLastError());
     }
     if (pl->n_short > 0) {
-        mark_failed_kernel<<<pl->n_short, 64, 0, st>>>(pl->d_short.as<ShortSeg>(), pl->n_short, o->status, nframes,
+        mark_failed_kernel<<<pl->n_short, 64, 0, st>>>(pl->d_short, pl->n_short, o->status, nframes,
                                                         o->char_start, o->char_end, o->char_score,
                                                         want_sec ? o->char_start_s : nullptr, o->char_end_s, o->char_score_r, o->path_token, o->path_logp);
         CUDA_TRY(cudaGetLastError());
@@ -687,9 +813,8 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
         const int threads = 128;
         const long long blocks = (pl->W + threads - 1) / threads;
         word_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-            pl->W, pl->d_word_seg.as<int>(), pl->d_seg_tok_base.as<long long>(), pl->d_wchar_off.as<long long>(),
-            pl->d_wchar_idx.as<int>(), o->status, o->char_start_s, o->char_end_s, o->char_score_r,
-            o->word_start_s, o->word_end_s, o->word_score);
+            pl->W, pl->d_word_seg, pl->d_seg_tok_base, pl->d_wchar_off, pl->d_wchar_idx, o->status, o->char_start_s,
+            o->char_end_s, o->char_score_r, o->word_start_s, o->word_end_s, o->word_score);
         CUDA_TRY(cudaGetLastError());
     }
     if (elapsed_dp_ms) {
@@ -699,34 +824,59 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     return WXB_OK;
 }
 
+extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *o, void *stream_, float *elapsed_dp_ms) {
+    return run_impl(pl, emis, nullptr, o, static_cast<cudaStream_t>(stream_), elapsed_dp_ms);
+}
+
 extern "C" int wxb_align_device(wxb_ctx *ctx, const wxb_batch *batch, const float *emissions_dev,
                                 const wxb_outputs *out_dev, void *stream) {
     wxb_plan *pl = nullptr;
     int rc = wxb_plan_create(ctx, batch, &pl);
     if (rc != WXB_OK) return rc;
     rc = wxb_plan_run(pl, emissions_dev, out_dev, stream, nullptr);
-    if (rc == WXB_OK) {
-        // the plan's device arrays must outlive the kernels that read them
-        cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-        if (e != cudaSuccess) rc = fail(WXB_ECUDA, "wxb_align_device: %s", cudaGetErrorString(e));
-    }
-    wxb_plan_destroy(pl);
+    wxb_plan_destroy(pl);         // synchronises the stream: the plan's device arrays outlive the kernels
     return rc;
 }
 
 extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis_host, const wxb_outputs *oh) {
     if (!c || !bt || !oh) return fail(WXB_EINVAL, "wxb_align_host: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    // 1. start moving the emissions before anything else: fixed-size row chunks on the copy stream, one
+    //    event per chunk.  Planning (host) and the kernels of earlier chunks overlap the rest of the copy.
+    int64_t rows = 0, chunk_rows = 0;
+    if (bt->n_segments > 0 && bt->frame_off && bt->vocab >= 1) {
+        rows = bt->frame_off[bt->n_segments];
+        if (rows > 0 && !emis_host) return fail(WXB_EINVAL, "wxb_align_host: emissions is NULL");
+        chunk_rows = std::max<int64_t>(1, static_cast<int64_t>(c->chunk_bytes / (4ull * bt->vocab)));
+    }
+    int n_chunks = 0;
+    if (rows > 0) {
+        const size_t V = static_cast<size_t>(bt->vocab);
+        CUDA_TRY(c->h_emis.ensure(static_cast<size_t>(rows) * V * 4));
+        n_chunks = static_cast<int>((rows + chunk_rows - 1) / chunk_rows);
+        while (static_cast<int>(c->ev_chunk.size()) < n_chunks) {
+            cudaEvent_t ev;
+            CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->ev_chunk.push_back(ev);
+        }
+        for (int k = 0; k < n_chunks; ++k) {
+            const int64_t r0 = k * chunk_rows, r1 = std::min(rows, r0 + chunk_rows);
+            CUDA_TRY(cudaMemcpyAsync(c->h_emis.as<float>() + r0 * V, emis_host + r0 * V, static_cast<size_t>(r1 - r0) * V * 4,
+                                     cudaMemcpyHostToDevice, c->copy));
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[k], c->copy));
+        }
+    }
+    // 2. plan while the copy engine works
     wxb_plan *pl = nullptr;
-    int rc = wxb_plan_create(c, bt, &pl);
-    if (rc != WXB_OK) return rc;
-    struct Guard { wxb_plan *p; ~Guard() { wxb_plan_destroy(p); } } guard{pl};
+    int rc = plan_create_impl(c, bt, chunk_rows, &pl);
+    if (rc != WXB_OK) { cudaStreamSynchronize(c->copy); return rc; }
+    struct Guard { wxb_plan *p; wxb_ctx *c; ~Guard() { cudaStreamSynchronize(c->copy); wxb_plan_destroy(p); } } guard{pl, c};
     if (pl->S == 0) return WXB_OK;
     const size_t S = static_cast<size_t>(pl->S), sN = static_cast<size_t>(std::max<int64_t>(pl->sum_N, 1));
     const size_t sT = static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)), W = static_cast<size_t>(std::max<int64_t>(pl->W, 1));
     const size_t V = static_cast<size_t>(pl->V);
     wxb_outputs od;
     memset(&od, 0, sizeof od);
-    CUDA_TRY(c->h_emis.ensure(sT * V * 4));
     CUDA_TRY(c->h_i32[0].ensure(S * 4)); od.status = c->h_i32[0].as<int32_t>();
     CUDA_TRY(c->h_i32[1].ensure(S * 4)); od.n_frames = c->h_i32[1].as<int32_t>();
     CUDA_TRY(c->h_i32[2].ensure(sN * 4)); od.char_start = c->h_i32[2].as<int32_t>();
@@ -752,8 +902,7 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
     if (oh->logprobs) { CUDA_TRY(c->h_f32[3].ensure(sT * V * 4)); od.logprobs = c->h_f32[3].as<float>(); }
 
     cudaStream_t st = c->main;
-    if (pl->sum_T > 0) CUDA_TRY(cudaMemcpyAsync(c->h_emis.p, emis_host, static_cast<size_t>(pl->sum_T) * V * 4, cudaMemcpyHostToDevice, st));
-    rc = wxb_plan_run(pl, c->h_emis.as<float>(), &od, st, nullptr);
+    rc = run_impl(pl, c->h_emis.as<float>(), n_chunks > 0 ? c->ev_chunk.data() : nullptr, &od, st, nullptr);
     if (rc != WXB_OK) return rc;
 #define WXB_D2H(field, count, type)                                                                   \
     if (oh->field && (count) > 0)                                                                     \
@@ -778,6 +927,7 @@ extern "C" int wxb_plan_debug_trace(wxb_plan *pl, uint64_t *rows, int64_t cap_ro
     if (!c->want_trace || !c->trace.p) return fail(WXB_EINVAL, "wxb_plan_debug_trace: create the ctx with WXB_TRACE=1 and run the plan first");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaDeviceSynchronize());
+    if (pl->host_descs.empty()) return fail(WXB_EINVAL, "wxb_plan_debug_trace: the plan was created without WXB_TRACE=1");
     const int n = static_cast<int>(std::min<int64_t>(pl->n_desc, cap_rows));
     std::vector<unsigned long long> raw(static_cast<size_t>(std::max(n, 1)) * 4);
     CUDA_TRY(cudaMemcpy(raw.data(), c->trace.p, static_cast<size_t>(n) * 32, cudaMemcpyDeviceToHost));

@@ -47,7 +47,6 @@ struct SegDesc {
 
 struct Params {
     const float *emis;
-    const int *tokens;      // [sum_N] token ids
     const int *tok4;        // [sum_N] token ids * 4 (byte offset inside an emission row)
     const SegDesc *segs;
     uint32_t *bits;         // choice words of a segment: word ((t/32)*W*K + w*K + slot)*32 + lane, bit 31-(t%32)
@@ -465,14 +464,14 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
     const int r = db.N - 32 * W * (K - 1);
     const long long wstep = static_cast<long long>(W) * K * 32;
     int status = 0;
-    int *cstart = p.c_start + db.tok_base;
     if (t_start == 0) {
         status = 1;                                  // empty walk -> for/else -> None
     } else {
-        int j = db.N;
+        int j = db.N;                                // current column (token j-1 is being located)
         int s = t_start - 1;                         // frame of the current point
-        bool done = false;
-        while (!done) {
+        int *cs_ptr = p.c_start + db.tok_base + (j - 1);     // where token j-1's entry frame goes
+        bool more = true;
+        while (more) {
             const int j0 = j;                        // window columns j0, j0-1, ..., j0-31
             const int w0 = s >> 5;                   // window words   w0, w0-1, w0-2, w0-3
             uint32_t wA = 0u, wB = 0u, wC = 0u, wD = 0u;
@@ -486,26 +485,31 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
                 if (w0 >= 2) wC = __ldcg(bp - 2 * wstep);
                 if (w0 >= 3) wD = __ldcg(bp - 3 * wstep);
             }
-            while (true) {
+            const int jmin = j0 - 31;                // leave the window below this column ...
+            const int smin = (w0 - 3) << 5;          // ... or below this frame
+            bool inside = true;
+            // One iteration per visited (column, word) pair, branch-free inside: either the token's
+            // entry frame is in this word (store it, move one column left) or the path stayed through
+            // the rest of the word (move to the previous word).
+            while (inside) {
                 const int dw = w0 - (s >> 5);        // 0..3 inside the window
-                const uint32_t mine = (dw == 0) ? wA : (dw == 1) ? wB : (dw == 2) ? wC : wD;
+                const uint32_t lo = (dw & 1) ? wB : wA;
+                const uint32_t hi = (dw & 1) ? wD : wC;
+                const uint32_t mine = (dw & 2) ? hi : lo;
                 const uint32_t word = __shfl_sync(FULL, mine, j0 - j);
                 // bit (31 - f%32) is frame f; shift so that bit 0 = frame s, bit q = frame s-q
                 const uint32_t m = word >> (31 - (s & 31));
-                if (m == 0u) {
-                    s = (s & ~31) - 1;               // stayed through the rest of this word
-                    if (s < 0) { status = 1; done = true; break; }
-                } else {
-                    const int sc = s - (__ffs(m) - 1);   // frame at which token j-1 was entered
-                    if (lane == 0) cstart[j - 1] = sc;
-                    --j;
-                    if (j == 0) { done = true; break; }
-                    s = sc - 1;
-                    if (s < 0) { status = 1; done = true; break; }
-                }
-                if (j < j0 - 31 || (s >> 5) < w0 - 3) break;     // left the window: fetch the next one
+                const bool found = (m != 0u);
+                const int sc = s - (__ffs(m) - 1);   // frame at which token j-1 was entered (if found)
+                if (found && lane == 0) *cs_ptr = sc;
+                cs_ptr -= found ? 1 : 0;
+                j -= found ? 1 : 0;
+                s = found ? sc - 1 : (s & ~31) - 1;
+                more = (j > 0) && (s >= 0);
+                inside = more && (j >= jmin) && (s >= smin);
             }
         }
+        status = (j == 0) ? 0 : 1;                   // ran out of frames before reaching token 0 -> None
     }
     if (lane == 0) {
         p.status[db.seg] = status;
