@@ -210,7 +210,7 @@ def run_ours(args):
         import multiprocessing as mp
         import torch
         cores = _host_cores()
-        n_sample = max(4 * cores, 64)
+        n_sample = min(max(16 * cores, 256), nseg)          # ~10-30 core-seconds of the Python reference path
         logp_s = torch.log_softmax(torch.from_numpy(batch.emissions[: int(batch.frame_off[n_sample])]), -1).numpy()
         with mp.get_context("fork").Pool(cores) as pool:
             cpu_reference_pass(batch, min(cores, n_sample), pool, logp_s)           # warm the workers
@@ -306,17 +306,20 @@ def run_ours(args):
                                    "~13.3 chars/s transcripts, raw logits in (fused log-softmax), iid N(0,9) logits",
                        "segments_per_gpu": nseg, "workload_id": args.workload, "audio_hours_per_gpu": batch.audio_seconds / 3600.0,
                        "cells_per_gpu": int(plan.cells), "emission_bytes_per_gpu": int(host_em.numel() * 4),
-                       "l2": "inputs (415 MB) larger than L2 (126 MB); no explicit flush",
+                       "l2": f"inputs ({host_em.numel() * 4 / 1e6:.0f} MB per step) larger than L2 (126 MB); no explicit flush",
                        "failed_segments": failed},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
-                         "kernel": "wxb::align_kernel<K,false> (11 concurrent launches, one per tokens-per-lane class)",
+                         "kernel": f"wxb::align_kernel<K,false>: {int(plan.launches) - 1} concurrent launches per step, one per "
+                                   "(warps, tokens-per-lane) class, timed together with CUDA events on the launching stream",
                          "kernel_ms": dp, "algorithmic_bytes_per_step": int(plan.alg_bytes),
-                         "note": "algorithmic bytes = sum(4*T*V + 20*N); the kernel is issue-bound, not HBM-bound (DESIGN.md)"},
+                         "note": "algorithmic bytes = sum(4*T*V + 20*N) per step; traffic = ncu dram read+write summed over the "
+                                 "step's align_kernel launches (profiles/); the recurrence is issue-bound, not HBM-bound (DESIGN.md 4.1)"},
             "e2e": {"value": audio_all / 3600.0 / (e2e_ms * 1e-3 / args.steps), "unit": UNIT,
                     "ms_per_step": e2e_ms / args.steps, "cells_per_s": cells_all / (e2e_ms * 1e-3 / args.steps),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "wxb_align_host (whisperx_b200.engine.AlignEngine.align_batch_host), pinned host buffers"},
+                    "api": "wxb_align_host (whisperx_b200.engine.AlignEngine.align_batch_host): pinned host buffers in and out, "
+                           "planning + chunked H2D + kernels + D2H inside the timed region"},
             "gpu_launches": int(plan.launches) * args.steps,
             "clocks": clocks,
         }

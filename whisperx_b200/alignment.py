@@ -180,6 +180,19 @@ def align(
     Same arguments, side effects (the four keys added to every input segment) and result as the
     reference; the per-segment "Failed to align segment" messages are printed for the same
     three soft failures (:199-207, :245-248)."""
+    grouped = align_grouped(transcript, model, align_model_metadata, audio, device, interpolate_method,
+                            return_char_alignments, print_progress, combined_progress)
+    aligned: List[dict] = [rec for group in grouped for rec in group]
+    word_segments: List[dict] = []
+    for seg in aligned:
+        word_segments += seg["words"]
+    return {"segments": aligned, "word_segments": word_segments}
+
+
+def align_grouped(transcript, model, align_model_metadata, audio, device, interpolate_method="nearest",
+                  return_char_alignments=False, print_progress=False, combined_progress=False) -> List[List[dict]]:
+    """align() with the output records still grouped by input segment (one list per input segment;
+    the reference concatenates them, :347).  Used by align() and by the multi-GPU front end."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("whisperx_b200.align() runs the alignment path on a CUDA (sm_100a) device only; "
@@ -229,7 +242,7 @@ def align(
         results = _align_batch(engine, [transcript[s] for s in run], logits, dictionary, lang, audio.shape[0])
 
     # 3. records, in input order
-    aligned: List[dict] = []
+    grouped: List[List[dict]] = []
     k = 0
     for sdx, seg in enumerate(transcript):
         why = verdict[sdx]
@@ -240,16 +253,12 @@ def align(
                 why = "backtrack failed, resorting to original..."
             else:
                 lay, cs, ce, sc, ws, we, wsc = r
-                aligned += assemble.assemble_segment(seg["text"], seg["clean_cdx"], lay, seg["sentence_spans"], lang,
-                                                     cs, ce, sc, ws, we, wsc, interpolate_method, return_char_alignments)
+                grouped.append(assemble.assemble_segment(seg["text"], seg["clean_cdx"], lay, seg["sentence_spans"], lang,
+                                                         cs, ce, sc, ws, we, wsc, interpolate_method, return_char_alignments))
                 continue
         print(f'Failed to align segment ("{seg["text"]}"): {why}')
-        aligned.append(plain[sdx])
-
-    word_segments: List[dict] = []
-    for seg in aligned:
-        word_segments += seg["words"]
-    return {"segments": aligned, "word_segments": word_segments}
+        grouped.append([plain[sdx]])
+    return grouped
 
 
 def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], dictionary: dict, lang: str,
