@@ -41,6 +41,11 @@ def full(tag, rep):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
+    # the capture window may straddle two steps: keep one launch per (kernel, block, grid) class
+    seen = {}
+    for r in data:
+        seen[(r[idx["Kernel Name"]], r[idx["Block Size"]], r[idx["Grid Size"]])] = r
+    data = list(seen.values())
     want = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread", "regs"),
             ("launch__occupancy_limit_registers", "occ lim regs (CTAs)"), ("launch__occupancy_limit_shared_mem", "occ lim smem (CTAs)"),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
