@@ -20,4 +20,4 @@ for kt in (2, 3, 4, 5, 6, 7, 8):
         ms.append(out.extra["dp_ms"])
     print(f"{wl} k_target={kt}: launches={plan.launches} dp_ms={np.median(ms[2:]):.3f} -> {plan.cells/np.median(ms[2:])/1e6:.1f} Gcells/s failed={int(out.status.sum())}")
     plan.close()
-eng._lib.wxb_set_k_target(6)
+eng._lib.wxb_set_k_target(-1)

@@ -78,7 +78,7 @@ def test_pairwise_sum_matches_numpy():
 def test_tokens_per_lane_buckets():
     lib = N.load()
     shape = lambda n: (lib.wxb_segment_warps(n), lib.wxb_tokens_per_lane(n))
-    assert lib.wxb_set_k_target(0) == 5                    # default: fewest warps with K <= 5
+    assert lib.wxb_set_k_target(0) == 0                    # default: chosen per batch
     lib.wxb_set_k_target(6)
     assert shape(0) == (0, 0)
     assert shape(1) == (1, 1) and shape(32) == (1, 1) and shape(33) == (1, 2) and shape(192) == (1, 6)
@@ -86,7 +86,7 @@ def test_tokens_per_lane_buckets():
     assert shape(31 * 32 * 8) == (31, 8) and shape(31 * 32 * 8 + 1) == (-1, -1)
     assert lib.wxb_set_k_target(4) == 6
     assert shape(128) == (1, 4) and shape(129) == (2, 3) and shape(400) == (4, 4)
-    assert lib.wxb_set_k_target(5) == 4
+    assert lib.wxb_set_k_target(-1) == 4 and lib.wxb_set_k_target(0) == 0
     assert shape(160) == (1, 5) and shape(161) == (2, 3) and shape(400) == (3, 5)
 
 

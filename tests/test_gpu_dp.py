@@ -127,7 +127,7 @@ def test_k_target_sweep(engine, k_target):
     try:
         spec, res = run(engine, cases, 29, 0, align=4, want=("path", "final_col", "trellis"))
     finally:
-        lib.wxb_set_k_target(old)
+        lib.wxb_set_k_target(old if old > 0 else -1)
     check_against_oracle(spec, res, cases, 0, full=True)
 
 

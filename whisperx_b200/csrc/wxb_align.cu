@@ -306,7 +306,7 @@ struct wxb_ctx {
     DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
 };
 
-struct Bucket { int K; int W; int NB; size_t smem; int first; int count; long long cost; int maxT; int chunk; };
+struct Bucket { int K; int W; int NB; size_t smem; int first; int count; long long cost; int maxT; int chunk; int fin_first; int fin_count; };
 
 struct wxb_plan {
     wxb_ctx *ctx = nullptr;
@@ -331,11 +331,32 @@ struct wxb_plan {
 
 // Warps and tokens-per-lane for a transcript of n tokens: as few compute warps as keep K <= k_target
 // (more columns per lane amortise the per-frame overhead; more warps shorten the segment's latency).
-static int g_k_target = 5;
+static int g_k_target = 0;        // 0 = chosen per batch (see pick_k_target); 1..KMAX = forced
 
-static bool shape_of(long long n, int *W, int *K) {
+// Few columns per lane (more warps per segment) shorten a segment's latency, which is what bounds a
+// batch whose longest segments are a large part of the makespan; many columns per lane spend fewer
+// issue slots per cell, which is what bounds a batch that fills the GPU several times over.
+// frames_x_warps(kt) / capacity is the number of frame-times the batch needs at k_target kt; if that
+// is at least twice the longest segment, the tail does not matter and the efficient shape wins.
+static int pick_k_target(const int64_t *tok_off, const int64_t *frame_off, const int32_t *frame_len, int64_t S, int sm_count) {
+    const int kt_wide = KMAX, kt_narrow = 5;
+    double work = 0.0;
+    long long tmax = 0;
+    for (int64_t s = 0; s < S; ++s) {
+        const long long n = tok_off[s + 1] - tok_off[s];
+        const long long t = frame_len ? frame_len[s] : frame_off[s + 1] - frame_off[s];
+        if (n <= 0 || n > t) continue;
+        work += static_cast<double>(t) * static_cast<double>((n + 32 * kt_wide - 1) / (32 * kt_wide));
+        tmax = std::max(tmax, t);
+    }
+    const double capacity = 24.0 * sm_count;          // resident compute warps
+    return (tmax > 0 && work / capacity >= 2.0 * static_cast<double>(tmax)) ? kt_wide : kt_narrow;
+}
+
+static bool shape_of(long long n, int *W, int *K, int k_target = 0) {
     if (n <= 0) return false;
-    long long w = (n + 32ll * g_k_target - 1) / (32ll * g_k_target);
+    if (k_target <= 0) k_target = g_k_target > 0 ? g_k_target : 5;
+    long long w = (n + 32ll * k_target - 1) / (32ll * k_target);
     if (w > WMAX) w = WMAX;
     const long long k = (n + 32 * w - 1) / (32 * w);
     if (k > KMAX) return false;
@@ -389,6 +410,7 @@ extern "C" int wxb_segment_warps(int32_t n_tokens) {
 extern "C" int wxb_set_k_target(int k_target) {
     const int old = g_k_target;
     if (k_target > 0) g_k_target = std::max(1, std::min(KMAX, k_target));
+    if (k_target < 0) g_k_target = 0;            // back to the per-batch choice
     return old;
 }
 
@@ -529,6 +551,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     long long trellis_off = 0;
     int wmax = 1;
     const bool no_shortcut = (bt->flags & WXB_F_NO_SHORTCUT) != 0;
+    const int k_target = g_k_target > 0 ? g_k_target : pick_k_target(to, fo, bt->frame_len, S, ctx->sm_count);
     pl->chunk_row.push_back(0);
     if (chunk_rows > 0)
         for (int64_t r = chunk_rows; r < fo[S]; r += chunk_rows) pl->chunk_row.push_back(r);
@@ -541,7 +564,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         const long long this_trellis = trellis_off;
         trellis_off += static_cast<long long>(T + 1) * (N + 1);
         int K = -1, Wc = 0;
-        const bool fits = shape_of(N, &Wc, &K);
+        const bool fits = shape_of(N, &Wc, &K, k_target);
         if (N == 0 || (N > T && (!no_shortcut || !fits))) {
             shorts.push_back({to[s], fo[s], N, T, static_cast<int>(s), 0});
             continue;
@@ -573,16 +596,19 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         return a.T > b.T;
     });
     long long bits = 0;
+    int fin_next = 0;               // finalize work items (128 tokens each) are laid out in descriptor order
     for (size_t i = 0; i < descs.size(); ++i) {
         descs[i].bits_off = bits;
         bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].W * descs[i].K * 32;
         if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W || descs[i].pad != descs[i - 1].pad) {
-            Bucket b{descs[i].K, descs[i].W, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad};
+            Bucket b{descs[i].K, descs[i].W, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad, fin_next, 0};
             b.NB = pick_ring(b.W, pl->TE, pl->V, &b.smem);
             pl->buckets.push_back(b);
         }
         pl->buckets.back().count += 1;
         pl->buckets.back().cost += static_cast<long long>(descs[i].T) * descs[i].K * descs[i].W;
+        pl->buckets.back().fin_count += (descs[i].N + 127) / 128;
+        fin_next += (descs[i].N + 127) / 128;
     }
     pl->bits_words = bits;
     // launch order = placement priority: inside a chunk, classes holding the longest segments go
@@ -698,7 +724,9 @@ extern "C" void wxb_plan_destroy(wxb_plan *plan) {
 
 extern "C" int wxb_plan_launch_count(const wxb_plan *plan) {
     if (!plan) return 0;
-    return static_cast<int>(plan->buckets.size()) + (plan->n_fin_blocks > 0 ? 1 : 0) + (plan->n_short > 0 ? 1 : 0) + (plan->has_words ? 1 : 0);
+    int n = (plan->n_short > 0 ? 1 : 0) + (plan->has_words ? 1 : 0);
+    for (const Bucket &b : plan->buckets) n += 1 + (b.fin_count > 0 ? 1 : 0);      // align_kernel + its finalize_kernel
+    return n;
 }
 
 extern "C" int wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg_bytes, int64_t *n_shortcut) {
@@ -774,9 +802,16 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     CUDA_TRY(cudaStreamWaitEvent(st, pl->arena->uploaded, 0));     // the plan's metadata upload (ctx stream)
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t0, st));
     const int nb = static_cast<int>(pl->buckets.size());
+    // every class's finalize_kernel follows its align_kernel on the same stream, so it overlaps the
+    // other classes' recurrences instead of running after all of them
+    auto finalize = [&](const Bucket &b, cudaStream_t s) -> cudaError_t {
+        if (b.fin_count > 0) finalize_kernel<<<b.fin_count, 128, 0, s>>>(P, pl->d_fin + b.fin_first);
+        return cudaGetLastError();
+    };
     if (nb == 1 && !chunk_ready) {
         const Bucket &b = pl->buckets[0];
         CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, st, debug));
+        CUDA_TRY(finalize(b, st));
     } else if (nb >= 1) {
         // classes are independent: fork onto side streams so that every SM sees a mix of them
         const int used = std::min(nb, c->side_streams);
@@ -792,6 +827,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
                 seen_chunk[si] = b.chunk;
             }
             CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, c->side[si], debug));
+            CUDA_TRY(finalize(b, c->side[si]));
         }
         for (int i = 0; i < used; ++i) {
             CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));
@@ -799,10 +835,6 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
         }
     }
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t1, st));
-    if (pl->n_fin_blocks > 0) {
-        finalize_kernel<<<pl->n_fin_blocks, 128, 0, st>>>(P, pl->d_fin);
-        CUDA_TRY(cudaGetLastError());
-    }
     if (pl->n_short > 0) {
         mark_failed_kernel<<<pl->n_short, 64, 0, st>>>(pl->d_short, pl->n_short, o->status, nframes,
                                                         o->char_start, o->char_end, o->char_score,

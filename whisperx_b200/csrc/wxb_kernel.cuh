@@ -356,7 +356,31 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
         int t = 0;                      // frames consumed so far == current trellis row
         int b = -1;                     // ring position and lap parity of the current tile
         uint32_t ph = 0;
-        for (int tau = 0; tau < ntiles; ++tau) {
+        // Trellis column j is -inf in every row t < j (:369), so until frame `first column of this warp`
+        // all of the warp's cells are -inf and all of its choice bits 0 (-inf > -inf is false): whole
+        // tiles below that frame are passed on without running the recurrence.
+        const int g0 = wi * 32;
+        const int col0w = (g0 < r) ? g0 * K : r * K + (g0 - r) * (K - 1);
+        const int skip_tiles = (!DEBUG && TE == 32) ? min(col0w >> 5, ntiles) : 0;
+        int tau = 0;
+        for (; tau < skip_tiles; ++tau) {
+            ++b;
+            const bool wrap = (b == NB);
+            b = wrap ? 0 : b;
+            ph ^= wrap ? 1u : 0u;
+            const int n = min(TE, T - tau * TE);
+            mbar_wait(wait_bar0 + 8u * b, ph);
+            if (lane < n) sts_f32x2(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * 8u, -INFINITY, 0.0f);
+            if (n == 32) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) bits_w[i * 32] = 0u;
+                bits_w += bits_step;
+            }
+            t += n;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(next_bar0 + 8u * b);
+        }
+        for (; tau < ntiles; ++tau) {
             // branch-free ring step: a select keeps b / ph (and every address derived from them) in
             // uniform registers, an `if` does not
             ++b;
