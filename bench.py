@@ -310,8 +310,8 @@ def run_ours(args):
                        "failed_segments": failed},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
-                         "kernel": f"wxb::align_kernel<K,false>: {int(plan.launches) - 1} concurrent launches per step, one per "
-                                   "(warps, tokens-per-lane) class, timed together with CUDA events on the launching stream",
+                         "kernel": "wxb::align_kernel<K,false> (+ its finalize_kernel): one launch per (warps, tokens-per-lane) class, "
+                                   "run concurrently on side streams and timed together with CUDA events on the launching stream",
                          "kernel_ms": dp, "algorithmic_bytes_per_step": int(plan.alg_bytes),
                          "note": "algorithmic bytes = sum(4*T*V + 20*N) per step; traffic = ncu dram read+write summed over the "
                                  "step's align_kernel launches (profiles/); the recurrence is issue-bound, not HBM-bound (DESIGN.md 4.1)"},

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -40,6 +41,14 @@ __global__ void mark_failed_kernel(const ShortSeg *list, int n, int *status, int
     }
     if (path_tok)
         for (int f = threadIdx.x; f < s.T; f += blockDim.x) { path_tok[s.frame_base + f] = -1; path_logp[s.frame_base + f] = 0.0f; }
+}
+
+// Plan metadata upload by the SMs instead of the copy engine: wxb_align_host has the host->device
+// engine busy with the emission stream for milliseconds, and a DMA of the (small) metadata would
+// queue behind it.  `src` is pinned, mapped host memory; 16-byte loads over PCIe.
+__global__ void __launch_bounds__(256) upload_kernel(uint4 *dst, const uint4 *src, size_t n16) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
 }
 
 // ---- phase 3 as its own kernel: one thread per token of every segment ----
@@ -112,6 +121,7 @@ __global__ void word_reduce_kernel(long long W, const int *word_seg, const long 
                                    const long long *wchar_off, const int *wchar_idx, const int *status,
                                    const double *c_start_s, const double *c_end_s, const double *c_score_r,
                                    double *w_start, double *w_end, double *w_score) {
+    // (the caller shifts word_seg / wchar_off / w_* to the first word of the range it wants reduced)
     const long long w = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (w >= W) return;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -263,7 +273,7 @@ struct DevBuf {
 // One device allocation mirrored by one pinned host buffer: a plan's metadata is assembled in the
 // mirror and goes up in a single cudaMemcpyAsync.  Arenas are pooled per context (grow-only).
 struct Arena {
-    unsigned char *dev = nullptr, *host = nullptr;
+    unsigned char *dev = nullptr, *host = nullptr, *host_dev = nullptr;    // host_dev: device-side address of `host`
     size_t cap = 0;
     cudaEvent_t uploaded = nullptr;
     cudaError_t ensure(size_t bytes) {
@@ -276,15 +286,16 @@ struct Arena {
         const size_t want = bytes + bytes / 4 + 4096;
         cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dev), want);
         if (e != cudaSuccess) { dev = nullptr; return e; }
-        e = cudaHostAlloc(reinterpret_cast<void **>(&host), want, cudaHostAllocDefault);
-        if (e != cudaSuccess) { cudaFree(dev); dev = nullptr; host = nullptr; return e; }
+        e = cudaHostAlloc(reinterpret_cast<void **>(&host), want, cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&host_dev), host, 0);
+        if (e != cudaSuccess) { cudaFree(dev); if (host) cudaFreeHost(host); dev = host = host_dev = nullptr; return e; }
         cap = want;
         return cudaSuccess;
     }
     void release_mem() {
         if (dev) cudaFree(dev);
         if (host) cudaFreeHost(host);
-        dev = host = nullptr; cap = 0;
+        dev = host = host_dev = nullptr; cap = 0;
     }
     void release() { release_mem(); if (uploaded) cudaEventDestroy(uploaded); uploaded = nullptr; }
 };
@@ -294,13 +305,16 @@ struct wxb_ctx {
     int sm_count = 0;
     cudaStream_t main = nullptr;              // used by wxb_align_host and for plan uploads
     cudaStream_t copy = nullptr;              // host->device emission chunks (wxb_align_host)
+    cudaStream_t d2h = nullptr;               // per-chunk word reduction + device->host result copies (wxb_align_host)
+    cudaEvent_t ev_d2h = nullptr;
+    cudaEvent_t ev_dbg[3] = {};               // WXB_DEBUG_TIMING: kernels joined / results on the host / per-chunk
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<cudaEvent_t> ev_chunk;        // one per emission chunk in flight
     DevBuf bits, p0, rowmax, rowlse, nframes_scratch, trace;
     int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
     bool want_trace = false;                  // WXB_TRACE=1
-    size_t chunk_bytes = 128u << 20;          // WXB_CHUNK_MB: emission bytes per pipelined H2D chunk
+    size_t chunk_bytes = 64u << 20;           // WXB_CHUNK_MB: emission bytes per pipelined H2D chunk
     std::vector<Arena *> arena_pool;          // metadata arenas of destroyed plans, ready for reuse
     // wxb_align_host staging
     DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
@@ -316,6 +330,7 @@ struct wxb_plan {
     bool has_sec = false, has_words = false, has_round_np = false;
     std::vector<Bucket> buckets;              // chunk-major, longest segments first inside a chunk
     std::vector<int64_t> chunk_row;           // [n_chunks+1] emission row range of each chunk
+    std::vector<int64_t> chunk_seg;           // [n_chunks+1] input-segment range whose last row lies in each chunk
     int n_short = 0;
     long long bits_words = 0, trellis_floats = 0, cells = 0, alg_bytes = 0;
     int n_fin_blocks = 0, n_desc = 0;
@@ -436,6 +451,9 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming);
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev_dbg[i]);
     for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
@@ -462,6 +480,9 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     for (cudaEvent_t ev : c->ev_chunk) cudaEventDestroy(ev);
     if (c->main) cudaStreamDestroy(c->main);
     if (c->copy) cudaStreamDestroy(c->copy);
+    if (c->d2h) cudaStreamDestroy(c->d2h);
+    if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
+    for (int i = 0; i < 3; ++i) if (c->ev_dbg[i]) cudaEventDestroy(c->ev_dbg[i]);
     for (int i = 0; i < NSIDE; ++i) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
@@ -495,7 +516,7 @@ static void plan_free(wxb_plan *pl) {
 // chunk_rows = 0: one chunk (the emissions are already resident).  Otherwise the emission matrix
 // arrives in chunks of chunk_rows rows (wxb_align_host starts those copies before planning) and a
 // segment belongs to the chunk that holds its last row: its kernels wait for that chunk only.
-static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_rows, wxb_plan **out) {
+static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_rows, wxb_plan **out, bool copy_engine_busy = false) {
     if (!ctx || !bt || !out) return fail(WXB_EINVAL, "wxb_plan_create: NULL argument");
     *out = nullptr;
     const int64_t S = bt->n_segments;
@@ -557,10 +578,14 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         for (int64_t r = chunk_rows; r < fo[S]; r += chunk_rows) pl->chunk_row.push_back(r);
     pl->chunk_row.push_back(fo[S]);
     const int n_chunks = static_cast<int>(pl->chunk_row.size()) - 1;
+    pl->chunk_seg.assign(static_cast<size_t>(n_chunks) + 1, S);
+    pl->chunk_seg[0] = 0;
+    int chunk_prev = 0;
     for (int64_t s = 0; s < S; ++s) {
         const int T = bt->frame_len ? bt->frame_len[s] : static_cast<int>(fo[s + 1] - fo[s]);
         const int N = static_cast<int>(to[s + 1] - to[s]);
         const int chunk = chunk_rows > 0 ? static_cast<int>(std::min<int64_t>((fo[s] + std::max(T, 1) - 1) / chunk_rows, n_chunks - 1)) : 0;
+        for (; chunk_prev < chunk; ++chunk_prev) pl->chunk_seg[chunk_prev + 1] = s;     // last rows are non-decreasing in s
         const long long this_trellis = trellis_off;
         trellis_off += static_cast<long long>(T + 1) * (N + 1);
         int K = -1, Wc = 0;
@@ -690,7 +715,14 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         memcpy(h + o_woff, bt->wchar_off, (nW + 1) * 8);
         if (n_wc) memcpy(h + o_widx, bt->wchar_idx, n_wc * 4);
     }
-    CUDA_TRY(cudaMemcpyAsync(ar->dev, ar->host, off, cudaMemcpyHostToDevice, ctx->main));
+    if (copy_engine_busy) {
+        const size_t n16 = (off + 15) / 16;               // the arena is padded to 256 bytes
+        upload_kernel<<<static_cast<unsigned>(std::min<size_t>((n16 + 255) / 256, 4 * static_cast<size_t>(ctx->sm_count))), 256, 0, ctx->main>>>(
+            reinterpret_cast<uint4 *>(ar->dev), reinterpret_cast<const uint4 *>(ar->host_dev), n16);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(ar->dev, ar->host, off, cudaMemcpyHostToDevice, ctx->main));
+    }
     CUDA_TRY(cudaEventRecord(ar->uploaded, ctx->main));
     unsigned char *dv = ar->dev;
     pl->d_segs = reinterpret_cast<SegDesc *>(dv + o_segs);
@@ -741,8 +773,16 @@ extern "C" int wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg
 // chunk_ready != nullptr: pipelined host path — chunk c of the emissions is on its way to `emis`
 // on the copy stream and chunk_ready[c] fires when it has landed; the kernels of a segment wait
 // for the chunk that holds its last row.
+// With a sink (wxb_align_host), the results of a chunk's segments go back to the host as soon as that
+// chunk's kernels are done, on their own stream: the device->host copies overlap the rest of the
+// host->device emission stream (PCIe is full duplex).
+struct HostSink {
+    const wxb_outputs *host;        // caller's buffers
+    const int64_t *tok_off, *word_off, *frame_off;
+};
+
 static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_ready, const wxb_outputs *o, cudaStream_t st,
-                    float *elapsed_dp_ms) {
+                    float *elapsed_dp_ms, const HostSink *sink = nullptr) {
     if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
     if (pl->S == 0) { if (elapsed_dp_ms) *elapsed_dp_ms = 0.f; return WXB_OK; }
     if (!o->status || !o->char_start || !o->char_end || !o->char_score)
@@ -808,6 +848,21 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
         if (b.fin_count > 0) finalize_kernel<<<b.fin_count, 128, 0, s>>>(P, pl->d_fin + b.fin_first);
         return cudaGetLastError();
     };
+    if (pl->n_short > 0) {
+        mark_failed_kernel<<<pl->n_short, 64, 0, st>>>(pl->d_short, pl->n_short, o->status, nframes,
+                                                        o->char_start, o->char_end, o->char_score,
+                                                        want_sec ? o->char_start_s : nullptr, o->char_end_s, o->char_score_r, o->path_token, o->path_logp);
+        CUDA_TRY(cudaGetLastError());
+    }
+    auto reduce_words = [&](int64_t w0, int64_t w1, cudaStream_t s) -> cudaError_t {
+        if (!want_words || w1 <= w0) return cudaSuccess;
+        const int threads = 128;
+        const long long blocks = (w1 - w0 + threads - 1) / threads;
+        word_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+            w1 - w0, pl->d_word_seg + w0, pl->d_seg_tok_base, pl->d_wchar_off + w0, pl->d_wchar_idx, o->status, o->char_start_s,
+            o->char_end_s, o->char_score_r, o->word_start_s + w0, o->word_end_s + w0, o->word_score + w0);
+        return cudaGetLastError();
+    };
     if (nb == 1 && !chunk_ready) {
         const Bucket &b = pl->buckets[0];
         CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, st, debug));
@@ -817,11 +872,41 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
         const int used = std::min(nb, c->side_streams);
         CUDA_TRY(cudaEventRecord(c->ev_fork, st));
         for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+        if (sink) CUDA_TRY(cudaStreamWaitEvent(c->d2h, c->ev_fork, 0));
         int seen_chunk[NSIDE];
         for (int i = 0; i < NSIDE; ++i) seen_chunk[i] = -1;
+        auto drain_chunk = [&](int chunk) -> int {      // results of the chunk's segments -> host, on the d2h stream
+            for (int i = 0; i < used; ++i) {
+                CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));
+                CUDA_TRY(cudaStreamWaitEvent(c->d2h, c->ev_join[i], 0));
+            }
+            const int64_t s0 = pl->chunk_seg[chunk], s1 = pl->chunk_seg[chunk + 1];
+            if (s1 <= s0) return WXB_OK;
+            const int64_t k0 = sink->tok_off[s0], k1 = sink->tok_off[s1];
+            const int64_t w0 = pl->has_words ? sink->word_off[s0] : 0, w1 = pl->has_words ? sink->word_off[s1] : 0;
+            const int64_t f0 = sink->frame_off[s0], f1 = sink->frame_off[s1];
+            CUDA_TRY(reduce_words(w0, w1, c->d2h));
+            const wxb_outputs *h = sink->host;
+#define WXB_D2H(field, lo, hi, type)                                                                          \
+            if (h->field && o->field && (hi) > (lo))                                                          \
+                CUDA_TRY(cudaMemcpyAsync(h->field + (lo), o->field + (lo), static_cast<size_t>((hi) - (lo)) * sizeof(type), \
+                                         cudaMemcpyDeviceToHost, c->d2h));
+            WXB_D2H(status, s0, s1, int32_t) WXB_D2H(n_frames, s0, s1, int32_t)
+            WXB_D2H(char_start, k0, k1, int32_t) WXB_D2H(char_end, k0, k1, int32_t) WXB_D2H(char_score, k0, k1, double)
+            WXB_D2H(char_start_s, k0, k1, double) WXB_D2H(char_end_s, k0, k1, double) WXB_D2H(char_score_r, k0, k1, double)
+            WXB_D2H(word_start_s, w0, w1, double) WXB_D2H(word_end_s, w0, w1, double) WXB_D2H(word_score, w0, w1, double)
+            WXB_D2H(path_token, f0, f1, int32_t) WXB_D2H(path_logp, f0, f1, float)
+#undef WXB_D2H
+            return WXB_OK;
+        };
+        int cur_chunk = nb > 0 ? pl->buckets[0].chunk : 0;
         for (int i = 0; i < nb; ++i) {
             const Bucket &b = pl->buckets[i];
             const int si = i % used;
+            if (sink && b.chunk != cur_chunk) {
+                for (int ch = cur_chunk; ch < b.chunk; ++ch) { int rc = drain_chunk(ch); if (rc != WXB_OK) return rc; }
+                cur_chunk = b.chunk;
+            }
             if (chunk_ready && seen_chunk[si] < b.chunk) {
                 CUDA_TRY(cudaStreamWaitEvent(c->side[si], chunk_ready[b.chunk], 0));
                 seen_chunk[si] = b.chunk;
@@ -829,26 +914,23 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
             CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, c->side[si], debug));
             CUDA_TRY(finalize(b, c->side[si]));
         }
+        if (sink) {
+            const int n_chunks = static_cast<int>(pl->chunk_seg.size()) - 1;
+            for (int ch = cur_chunk; ch < n_chunks; ++ch) { int rc = drain_chunk(ch); if (rc != WXB_OK) return rc; }
+            CUDA_TRY(cudaEventRecord(c->ev_dbg[1], c->d2h));
+            CUDA_TRY(cudaEventRecord(c->ev_d2h, c->d2h));
+        }
         for (int i = 0; i < used; ++i) {
             CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));
             CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[i], 0));
         }
+        if (sink) {
+            CUDA_TRY(cudaEventRecord(c->ev_dbg[0], st));          // all kernels done
+            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_d2h, 0));
+        }
     }
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t1, st));
-    if (pl->n_short > 0) {
-        mark_failed_kernel<<<pl->n_short, 64, 0, st>>>(pl->d_short, pl->n_short, o->status, nframes,
-                                                        o->char_start, o->char_end, o->char_score,
-                                                        want_sec ? o->char_start_s : nullptr, o->char_end_s, o->char_score_r, o->path_token, o->path_logp);
-        CUDA_TRY(cudaGetLastError());
-    }
-    if (want_words) {
-        const int threads = 128;
-        const long long blocks = (pl->W + threads - 1) / threads;
-        word_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-            pl->W, pl->d_word_seg, pl->d_seg_tok_base, pl->d_wchar_off, pl->d_wchar_idx, o->status, o->char_start_s,
-            o->char_end_s, o->char_score_r, o->word_start_s, o->word_end_s, o->word_score);
-        CUDA_TRY(cudaGetLastError());
-    }
+    if (!sink) CUDA_TRY(reduce_words(0, pl->W, st));
     if (elapsed_dp_ms) {
         CUDA_TRY(cudaEventSynchronize(c->ev_t1));
         CUDA_TRY(cudaEventElapsedTime(elapsed_dp_ms, c->ev_t0, c->ev_t1));
@@ -873,6 +955,9 @@ extern "C" int wxb_align_device(wxb_ctx *ctx, const wxb_batch *batch, const floa
 extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis_host, const wxb_outputs *oh) {
     if (!c || !bt || !oh) return fail(WXB_EINVAL, "wxb_align_host: NULL argument");
     CUDA_TRY(cudaSetDevice(c->device));
+    const bool timing = getenv("WXB_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     // 1. start moving the emissions before anything else: fixed-size row chunks on the copy stream, one
     //    event per chunk.  Planning (host) and the kernels of earlier chunks overlap the rest of the copy.
     int64_t rows = 0, chunk_rows = 0;
@@ -891,16 +976,20 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
             CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             c->ev_chunk.push_back(ev);
         }
+        if (timing) CUDA_TRY(cudaEventRecord(c->ev_t0, c->copy));
         for (int k = 0; k < n_chunks; ++k) {
             const int64_t r0 = k * chunk_rows, r1 = std::min(rows, r0 + chunk_rows);
             CUDA_TRY(cudaMemcpyAsync(c->h_emis.as<float>() + r0 * V, emis_host + r0 * V, static_cast<size_t>(r1 - r0) * V * 4,
                                      cudaMemcpyHostToDevice, c->copy));
             CUDA_TRY(cudaEventRecord(c->ev_chunk[k], c->copy));
         }
+        if (timing) CUDA_TRY(cudaEventRecord(c->ev_t1, c->copy));
     }
     // 2. plan while the copy engine works
+    const double t_copies = now();
     wxb_plan *pl = nullptr;
-    int rc = plan_create_impl(c, bt, chunk_rows, &pl);
+    int rc = plan_create_impl(c, bt, chunk_rows, &pl, /*copy_engine_busy=*/n_chunks > 0);
+    const double t_plan = now();
     if (rc != WXB_OK) { cudaStreamSynchronize(c->copy); return rc; }
     struct Guard { wxb_plan *p; wxb_ctx *c; ~Guard() { cudaStreamSynchronize(c->copy); wxb_plan_destroy(p); } } guard{pl, c};
     if (pl->S == 0) return WXB_OK;
@@ -934,20 +1023,38 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
     if (oh->logprobs) { CUDA_TRY(c->h_f32[3].ensure(sT * V * 4)); od.logprobs = c->h_f32[3].as<float>(); }
 
     cudaStream_t st = c->main;
-    rc = run_impl(pl, c->h_emis.as<float>(), n_chunks > 0 ? c->ev_chunk.data() : nullptr, &od, st, nullptr);
+    // results stream back per chunk when there is anything to run (see HostSink); otherwise in bulk below
+    const bool stream_back = !pl->buckets.empty();
+    HostSink sink{oh, bt->tok_off, bt->word_off, bt->frame_off};
+    rc = run_impl(pl, c->h_emis.as<float>(), n_chunks > 0 ? c->ev_chunk.data() : nullptr, &od, st, nullptr,
+                  stream_back ? &sink : nullptr);
     if (rc != WXB_OK) return rc;
 #define WXB_D2H(field, count, type)                                                                   \
     if (oh->field && (count) > 0)                                                                     \
         CUDA_TRY(cudaMemcpyAsync(oh->field, od.field, static_cast<size_t>(count) * sizeof(type), cudaMemcpyDeviceToHost, st));
-    WXB_D2H(status, pl->S, int32_t) WXB_D2H(n_frames, pl->S, int32_t)
-    WXB_D2H(char_start, pl->sum_N, int32_t) WXB_D2H(char_end, pl->sum_N, int32_t) WXB_D2H(char_score, pl->sum_N, double)
-    WXB_D2H(char_start_s, pl->sum_N, double) WXB_D2H(char_end_s, pl->sum_N, double) WXB_D2H(char_score_r, pl->sum_N, double)
-    WXB_D2H(word_start_s, pl->W, double) WXB_D2H(word_end_s, pl->W, double) WXB_D2H(word_score, pl->W, double)
-    WXB_D2H(path_token, pl->sum_T, int32_t) WXB_D2H(path_logp, pl->sum_T, float)
+    if (!stream_back) {
+        WXB_D2H(status, pl->S, int32_t) WXB_D2H(n_frames, pl->S, int32_t)
+        WXB_D2H(char_start, pl->sum_N, int32_t) WXB_D2H(char_end, pl->sum_N, int32_t) WXB_D2H(char_score, pl->sum_N, double)
+        WXB_D2H(char_start_s, pl->sum_N, double) WXB_D2H(char_end_s, pl->sum_N, double) WXB_D2H(char_score_r, pl->sum_N, double)
+        WXB_D2H(word_start_s, pl->W, double) WXB_D2H(word_end_s, pl->W, double) WXB_D2H(word_score, pl->W, double)
+        WXB_D2H(path_token, pl->sum_T, int32_t) WXB_D2H(path_logp, pl->sum_T, float)
+    }
     WXB_D2H(final_col, pl->sum_T + pl->S, float) WXB_D2H(trellis, pl->trellis_floats, float)
     WXB_D2H(logprobs, pl->sum_T * pl->V, float)
 #undef WXB_D2H
+    const double t_enq = now();
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (timing && rows > 0) {
+        float h2d_ms = 0.f;
+        cudaEventElapsedTime(&h2d_ms, c->ev_t0, c->ev_t1);
+        float k_ms = 0.f, d_ms = 0.f;
+        if (stream_back) { cudaEventElapsedTime(&k_ms, c->ev_t0, c->ev_dbg[0]); cudaEventElapsedTime(&d_ms, c->ev_t0, c->ev_dbg[1]); }
+        fprintf(stderr, "[wxb] align_host: since the first copy started: H2D done %.3f ms (%d chunks), kernels done %.3f ms, results on host %.3f ms\n",
+                h2d_ms, n_chunks, k_ms, d_ms);
+    }
+    if (timing)
+        fprintf(stderr, "[wxb] align_host: copies enqueued %.3f ms, plan %.3f ms, launches enqueued %.3f ms, sync %.3f ms, total %.3f ms\n",
+                t_copies - t_begin, t_plan - t_copies, t_enq - t_plan, now() - t_enq, now() - t_begin);
     return WXB_OK;
 }
 
