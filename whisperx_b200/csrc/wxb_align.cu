@@ -16,7 +16,7 @@
 #include <vector>
 
 namespace wxb {
-cudaError_t launch_align(int k, int warps, int nb, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug);
+cudaError_t launch_align(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug);
 
 constexpr int NSIDE = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -320,12 +320,12 @@ struct wxb_ctx {
     DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
 };
 
-struct Bucket { int K; int W; int NB; size_t smem; int first; int count; long long cost; int maxT; int chunk; int fin_first; int fin_count; };
+struct Bucket { int K; int W; int NB; int TE; size_t smem; int first; int count; long long cost; int maxT; int chunk; int fin_first; int fin_count; };
 
 struct wxb_plan {
     wxb_ctx *ctx = nullptr;
     int64_t S = 0, W = 0, sum_T = 0, sum_N = 0;
-    int V = 0, blank = 0, TE = 32;
+    int V = 0, blank = 0;
     uint32_t flags = 0;
     bool has_sec = false, has_words = false, has_round_np = false;
     std::vector<Bucket> buckets;              // chunk-major, longest segments first inside a chunk
@@ -390,22 +390,28 @@ static int tokens_per_lane(long long n) {
 // widest CTA of the batch still fits a ring of at least 2 tiles, else 16, 8, 4.
 static int g_tile_pref = 32;     // WXB_TILE_FRAMES (experiments): largest tile length tried
 
-static int pick_tile(int V, int Wmax, int *TE) {
+// Tile length (frames) and ring depth of a W-warp CTA over a V-wide vocabulary.  32-frame tiles
+// amortise the per-tile hand-offs best (measured: 16 costs +25 % on the V=29 benchmark), so they are
+// kept unless a CTA would then be so large that fewer than ~16 warps fit on an SM (wide vocabularies
+// with many warps); the ring is W+2 deep — every warp on its own tile plus one being filled — or
+// shallower if shared memory says so (any depth >= 2 is deadlock-free).  cp.async.bulk needs
+// 16-byte multiples, i.e. TE % 4 == 0.
+static int pick_shape(int W, int V, int *TE, int *NB, size_t *smem) {
     const int pref[4] = {32, 16, 8, 4};
-    for (int i = 0; i < 4; ++i) {
+    const int want_ctas = std::max(1, (16 + W) / (W + 1));
+    int chosen = -1;
+    for (int i = 0; i < 4 && chosen < 0; ++i) {
         if (pref[i] > g_tile_pref) continue;
-        if (smem_layout(Wmax, 2, pref[i], V).total <= static_cast<uint32_t>(SMEM_LIMIT)) { *TE = pref[i]; return 0; }
+        if (smem_layout(W, W + 2, pref[i], V).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     }
-    return -1;
-}
-
-// Ring depth for a W-warp CTA: W + 2 lets the producer run one tile ahead of a fully staggered
-// wavefront; fewer if shared memory says so (any depth >= 2 is deadlock-free).
-static int pick_ring(int W, int TE, int V, size_t *smem) {
+    for (int i = 0; i < 4 && chosen < 0; ++i)         // nothing reaches the occupancy target: the longest tile that fits at all
+        if (pref[i] <= g_tile_pref && smem_layout(W, 2, pref[i], V).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+    if (chosen < 0) return -1;
     int nb = W + 2;
-    while (nb > 2 && smem_layout(W, nb, TE, V).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
-    *smem = smem_layout(W, nb, TE, V).total;
-    return nb;
+    while (nb > 2 && smem_layout(W, nb, chosen, V).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
+    *TE = chosen; *NB = nb;
+    *smem = smem_layout(W, nb, chosen, V).total;
+    return 0;
 }
 
 // ------------------------------------------------------------------ ABI: lifecycle
@@ -496,7 +502,7 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
 extern "C" int wxb_get_limits(const wxb_ctx *ctx, wxb_limits *out) {
     if (!ctx || !out) return fail(WXB_EINVAL, "wxb_get_limits: NULL argument");
     int vmax = 1;
-    while (smem_layout(1, 2, 4, vmax + 1).total <= static_cast<uint32_t>(SMEM_LIMIT)) ++vmax;
+    while (smem_layout(1, 2, 4, vmax + 1).total <= static_cast<uint32_t>(SMEM_LIMIT)) ++vmax;       // one warp, 4-frame tiles
     out->max_vocab = vmax;
     out->max_tokens = 32 * WMAX * KMAX;
     out->tokens_per_lane = KMAX;
@@ -610,8 +616,11 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     }
     pl->trellis_floats = trellis_off;
     pl->n_short = static_cast<int>(shorts.size());
-    if (pick_tile(pl->V, wmax, &pl->TE) != 0)
-        return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory for a %d-warp segment", pl->V, SMEM_LIMIT, wmax);
+    {
+        int te, nbq; size_t sm;
+        if (pick_shape(wmax, pl->V, &te, &nbq, &sm) != 0)
+            return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory for a %d-warp segment", pl->V, SMEM_LIMIT, wmax);
+    }
     // one launch per (chunk, warps, tokens-per-lane) class; longest-first inside a class: the block
     // scheduler hands out CTAs in index order (LPT)
     std::stable_sort(descs.begin(), descs.end(), [](const SegDesc &a, const SegDesc &b) {
@@ -626,8 +635,8 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         descs[i].bits_off = bits;
         bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].W * descs[i].K * 32;
         if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W || descs[i].pad != descs[i - 1].pad) {
-            Bucket b{descs[i].K, descs[i].W, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad, fin_next, 0};
-            b.NB = pick_ring(b.W, pl->TE, pl->V, &b.smem);
+            Bucket b{descs[i].K, descs[i].W, 0, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad, fin_next, 0};
+            pick_shape(b.W, pl->V, &b.TE, &b.NB, &b.smem);
             pl->buckets.push_back(b);
         }
         pl->buckets.back().count += 1;
@@ -822,7 +831,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     P.p0 = c->p0.as<float>();
     P.rowmax = c->rowmax.as<float>();
     P.rowlse = c->rowlse.as<float>();
-    P.V = pl->V; P.blank = pl->blank; P.TE = pl->TE; P.is_logits = logits ? 1 : 0;
+    P.V = pl->V; P.blank = pl->blank; P.is_logits = logits ? 1 : 0;
     P.status = o->status; P.nframes = nframes;
     P.c_start = o->char_start; P.c_end = o->char_end; P.c_score = o->char_score;
     if (want_sec) {
@@ -865,7 +874,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     };
     if (nb == 1 && !chunk_ready) {
         const Bucket &b = pl->buckets[0];
-        CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, st, debug));
+        CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, st, debug));
         CUDA_TRY(finalize(b, st));
     } else if (nb >= 1) {
         // classes are independent: fork onto side streams so that every SM sees a mix of them
@@ -911,7 +920,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
                 CUDA_TRY(cudaStreamWaitEvent(c->side[si], chunk_ready[b.chunk], 0));
                 seen_chunk[si] = b.chunk;
             }
-            CUDA_TRY(launch_align(b.K, b.W, b.NB, P, b.first, b.count, b.smem, c->side[si], debug));
+            CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, c->side[si], debug));
             CUDA_TRY(finalize(b, c->side[si]));
         }
         if (sink) {

@@ -30,7 +30,7 @@ static cudaError_t configure(size_t smem) {
 }
 
 template <int K>
-static cudaError_t launch_one(int warps, int nb, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
+static cudaError_t launch_one(int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
     cudaError_t e = debug ? configure<K, true>(smem) : configure<K, false>(smem);
     if (e != cudaSuccess) return e;
     const int threads = 32 * (warps + 1);            // + the producer warp
@@ -39,23 +39,23 @@ static cudaError_t launch_one(int warps, int nb, const Params &p, int first, int
         cudaFuncAttributes fa;
         if (debug) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, align_kernel<K, true>, threads, smem); cudaFuncGetAttributes(&fa, align_kernel<K, true>); }
         else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, align_kernel<K, false>, threads, smem); cudaFuncGetAttributes(&fa, align_kernel<K, false>); }
-        fprintf(stderr, "[wxb] align_kernel<%d,%d> W=%d NB=%d: regs=%d smem=%zu grid=%d -> %d CTAs/SM\n", K, (int)debug, warps, nb, fa.numRegs, smem, count, nbk);
+        fprintf(stderr, "[wxb] align_kernel<%d,%d> W=%d NB=%d TE=%d: regs=%d smem=%zu grid=%d -> %d CTAs/SM\n", K, (int)debug, warps, nb, te, fa.numRegs, smem, count, nbk);
     }
-    if (debug) align_kernel<K, true><<<count, threads, smem, st>>>(p, first, nb);
-    else       align_kernel<K, false><<<count, threads, smem, st>>>(p, first, nb);
+    if (debug) align_kernel<K, true><<<count, threads, smem, st>>>(p, first, nb, te);
+    else       align_kernel<K, false><<<count, threads, smem, st>>>(p, first, nb, te);
     return cudaGetLastError();
 }
 
 template <int K>
-static cudaError_t dispatch(int k, int warps, int nb, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
-    if (k == K) return launch_one<K>(warps, nb, p, first, count, smem, st, debug);
-    if constexpr (K < KMAX) return dispatch<K + 1>(k, warps, nb, p, first, count, smem, st, debug);
+static cudaError_t dispatch(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
+    if (k == K) return launch_one<K>(warps, nb, te, p, first, count, smem, st, debug);
+    if constexpr (K < KMAX) return dispatch<K + 1>(k, warps, nb, te, p, first, count, smem, st, debug);
     else return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_align(int k, int warps, int nb, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
+cudaError_t launch_align(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
     if (warps < 1 || warps > WMAX || nb < 2) return cudaErrorInvalidValue;
-    return dispatch<1>(k, warps, nb, p, first, count, smem, st, debug);
+    return dispatch<1>(k, warps, nb, te, p, first, count, smem, st, debug);
 }
 
 }  // namespace wxb

@@ -53,7 +53,7 @@ struct Params {
     float *p0;              // [sum_T] expf(logp[t, 0])
     float *rowmax;          // [sum_T] (logits mode) row max
     float *rowlse;          // [sum_T] (logits mode) log(sum(exp(x - max)))
-    int V, blank, TE, is_logits;
+    int V, blank, is_logits, pad0;
     int *status, *nframes;
     int *c_start, *c_end;
     double *c_score, *c_start_s, *c_end_s, *c_score_r;
@@ -157,7 +157,7 @@ __device__ __forceinline__ void owner_of(int k, int r, int &g, int &slot) {
 #endif
 
 template <int K, bool DEBUG>
-__global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params p, const int seg_first, const int NB) {
+__global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params p, const int seg_first, const int NB, const int TE) {
     extern __shared__ __align__(128) unsigned char sm[];
     const int lane = threadIdx.x & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform (uniform registers for the
@@ -165,7 +165,7 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
     const int wi = __shfl_sync(FULL, static_cast<int>(threadIdx.x >> 5), 0);
     const int W = (blockDim.x >> 5) - 1;            // compute warps; warp W is the producer
     const SegDesc d = p.segs[seg_first + blockIdx.x];
-    const int T = d.T, N = d.N, V = p.V, TE = p.TE;
+    const int T = d.T, N = d.N, V = p.V;
     if (p.trace && threadIdx.x == 0) {
         uint32_t smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
