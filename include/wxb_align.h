@@ -158,6 +158,23 @@ int  wxb_backtrack_trellis_device(wxb_ctx *ctx, const float *trellis_dev, const 
                                   int32_t blank_id, int32_t *path_token_dev, float *path_logp_dev,
                                   int32_t *status_dev, int32_t *n_frames_dev, void *stream);
 
+/* ---- speaker assignment (whisperx/diarize.py:35-67, assign_word_speakers) ----
+ * For every query interval q (a segment or a word) the speaker whose diarization turns overlap it most:
+ *   intersection_d = min(d_end, q_end) - max(d_start, q_start)          (float64, diarize.py:39,52)
+ *   rows with intersection_d > 0 only, unless fill_nearest                (:42-45, :55-58)
+ *   per-speaker sums in row order (pandas groupby-sum: Kahan compensated), arg-max, ties to the
+ *   lowest speaker id (ids must follow the sorted label order, as groupby does)   (:47-48, :60-61)
+ * out_speaker[q] = speaker id, or -1 when no row qualifies.  n_speakers <= 64.
+ * _device: all pointers are device memory, work is enqueued on `stream`; _host: host pointers, blocking. */
+int  wxb_assign_speakers_device(wxb_ctx *ctx, const double *diar_start, const double *diar_end,
+                                const int32_t *diar_speaker, int64_t n_diar, int32_t n_speakers,
+                                const double *query_start, const double *query_end, int64_t n_query,
+                                int32_t fill_nearest, int32_t *out_speaker, void *stream);
+int  wxb_assign_speakers_host(wxb_ctx *ctx, const double *diar_start, const double *diar_end,
+                              const int32_t *diar_speaker, int64_t n_diar, int32_t n_speakers,
+                              const double *query_start, const double *query_end, int64_t n_query,
+                              int32_t fill_nearest, int32_t *out_speaker);
+
 /* ---- debug aid: per-CTA timeline of the last wxb_plan_run (ctx created with env WXB_TRACE=1) ----
  * rows: [cap_rows][8] = {t_begin_ns, t_forward_done_ns, t_end_ns, smid, T, N, K, segment}; returns the
  * number of rows written or a negative error code. */

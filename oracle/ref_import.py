@@ -62,6 +62,26 @@ def _install_nltk_stub() -> None:
 
 
 _CACHED = None
+_CACHED_DIARIZE = None
+
+
+def load_reference_diarize():
+    """The reference's `whisperx.diarize` module (unmodified).  pyannote is not installed, and the
+    module only needs its `Pipeline` name at import time, so an empty stand-in is registered."""
+    global _CACHED_DIARIZE
+    if _CACHED_DIARIZE is not None:
+        return _CACHED_DIARIZE
+    load_reference_alignment()                 # registers the bare `whisperx` package object
+    if "pyannote.audio" not in sys.modules:
+        pa = types.ModuleType("pyannote")
+        paa = types.ModuleType("pyannote.audio")
+        paa.Pipeline = type("Pipeline", (), {})
+        pa.audio = paa
+        sys.modules.setdefault("pyannote", pa)
+        sys.modules["pyannote.audio"] = paa
+    _CACHED_DIARIZE = importlib.import_module("whisperx.diarize")
+    return _CACHED_DIARIZE
+
 
 
 def load_reference_alignment():

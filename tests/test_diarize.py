@@ -1,0 +1,87 @@
+"""assign_word_speakers (whisperx/diarize.py:35-67): the oracle port against the reference's own
+outputs (tests/golden/diarize_cases.json, scripts/make_golden_diarize.py) on CPU, and the GPU drop-in
+against both."""
+import copy
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import ref_import, ref_port
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "diarize_cases.json")
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return json.load(open(GOLD))
+
+
+def test_port_matches_reference_golden(cases):
+    assert len(cases) == 8
+    for name, c in cases.items():
+        df = pd.DataFrame(c["turns"], columns=["start", "end", "speaker"])
+        got = ref_port.speakers_for(df, {"segments": copy.deepcopy(c["segments"])}, c["fill_nearest"])
+        assert got == c["result"], name
+        assert [float(x) for x in df.get("intersection", [])] == c["last_intersection"], name
+
+
+@pytest.mark.needs_reference
+def test_port_matches_live_reference(cases):
+    D = ref_import.load_reference_diarize()
+    c = cases["many_speakers_fill0"]
+    a = D.assign_word_speakers(pd.DataFrame(c["turns"]), {"segments": copy.deepcopy(c["segments"])})
+    b = ref_port.speakers_for(pd.DataFrame(c["turns"]), {"segments": copy.deepcopy(c["segments"])})
+    assert a == b == c["result"]
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_golden(engine, cases):
+    from whisperx_b200 import assign_word_speakers
+    for name, c in cases.items():
+        df = pd.DataFrame(c["turns"], columns=["start", "end", "speaker"])
+        tr = {"segments": copy.deepcopy(c["segments"])}
+        got = assign_word_speakers(df, tr, fill_nearest=c["fill_nearest"])
+        assert got is tr and got == c["result"], name
+        assert [float(x) for x in df.get("intersection", [])] == c["last_intersection"], name
+
+
+@pytest.mark.gpu
+def test_gpu_matches_port_on_a_long_recording(engine):
+    """A 1-hour shaped case: ~9,000 words against ~1,500 turns of 12 speakers, plus exact ties."""
+    from whisperx_b200 import assign_word_speakers
+    rng = np.random.default_rng(7)
+    t, turns = 0.0, []
+    for _ in range(1500):
+        s = max(t + float(rng.uniform(-1.0, 1.5)), 0.0)
+        d = float(rng.uniform(0.3, 5.0))
+        turns.append({"start": round(s, 3), "end": round(s + d, 3), "speaker": f"S{int(rng.integers(0, 12)):02d}"})
+        t = s + d
+    turns += [dict(x, speaker="S99") for x in turns[:40]]      # S99 ties with whoever owns those turns
+    segs, cur = [], 0.0
+    for i in range(120):
+        seg = {"start": cur, "end": cur + 30.0, "text": str(i), "words": []}
+        w = cur
+        while w < cur + 29.5:
+            wd = float(rng.uniform(0.1, 0.7))
+            seg["words"].append({"word": "w", "start": round(w, 3), "end": round(w + wd, 3)})
+            w += wd
+        segs.append(seg)
+        cur += 30.0
+    for fill in (False, True):
+        a = assign_word_speakers(pd.DataFrame(turns), {"segments": copy.deepcopy(segs)}, fill_nearest=fill)
+        b = ref_port.speakers_for(pd.DataFrame(turns), {"segments": copy.deepcopy(segs)}, fill)
+        assert a == b
+        assert sum("speaker" in w for s in a["segments"] for w in s["words"]) > 8000
+
+
+@pytest.mark.gpu
+def test_gpu_argument_checks(engine):
+    from whisperx_b200 import _native, assign_word_speakers
+    many = pd.DataFrame({"start": np.arange(70.0), "end": np.arange(70.0) + 1, "speaker": [f"S{i:03d}" for i in range(70)]})
+    with pytest.raises(_native.NativeError, match="at most 64"):
+        assign_word_speakers(many, {"segments": [{"start": 0.0, "end": 1.0, "text": "x"}]})
+    empty = {"segments": []}
+    assert assign_word_speakers(many, empty) is empty

@@ -11,7 +11,8 @@ timestamp reduction run in hand-written sm_100a CUDA kernels behind a C ABI
 """
 from .alignment import (Point, Segment, align, backtrack, get_trellis, load_align_model, load_audio,  # noqa: F401
                         merge_repeats, merge_words, set_sentence_splitter)
+from .diarize import assign_word_speakers  # noqa: F401
 from .engine import AlignEngine, BatchResult, BatchSpec, get_engine  # noqa: F401
 
 __all__ = ["load_align_model", "align", "load_audio", "get_trellis", "backtrack", "merge_repeats", "merge_words",
-           "Point", "Segment", "set_sentence_splitter", "AlignEngine", "BatchSpec", "BatchResult", "get_engine"]
+           "Point", "Segment", "set_sentence_splitter", "assign_word_speakers", "AlignEngine", "BatchSpec", "BatchResult", "get_engine"]

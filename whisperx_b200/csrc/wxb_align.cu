@@ -232,6 +232,51 @@ __global__ void __launch_bounds__(256) backtrack_trellis_kernel(const float *R, 
     *nframes = t_start;
 }
 
+// assign_word_speakers (whisperx/diarize.py:35-67): one thread per query interval, diarization turns
+// staged through shared memory in row order so that every per-speaker sum is accumulated exactly as
+// pandas' groupby-sum does (Kahan compensation, row order).
+constexpr int SPK_MAX = 64;
+constexpr int SPK_TILE = 256;
+__global__ void __launch_bounds__(128) assign_speakers_kernel(const double *d_start, const double *d_end, const int *d_spk,
+                                                              long long n_diar, int n_spk, const double *q_start,
+                                                              const double *q_end, long long n_query, int fill_nearest,
+                                                              int *out) {
+    __shared__ double s_start[SPK_TILE], s_end[SPK_TILE];
+    __shared__ int s_spk[SPK_TILE];
+    const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const bool live = q < n_query;
+    const double qs = live ? q_start[q] : 0.0, qe = live ? q_end[q] : 0.0;
+    double sum[SPK_MAX], comp[SPK_MAX];
+    for (int k = 0; k < n_spk; ++k) { sum[k] = 0.0; comp[k] = 0.0; }
+    unsigned long long seen = 0ull;              // speakers with at least one qualifying row
+    for (long long base = 0; base < n_diar; base += SPK_TILE) {
+        const int n = static_cast<int>(min(static_cast<long long>(SPK_TILE), n_diar - base));
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            s_start[i] = d_start[base + i]; s_end[i] = d_end[base + i]; s_spk[i] = d_spk[base + i];
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int i = 0; i < n; ++i) {
+            const double inter = fmin(s_end[i], qe) - fmax(s_start[i], qs);
+            if (fill_nearest || inter > 0.0) {
+                const int k = s_spk[i];
+                const double y = inter - comp[k];
+                const double t = sum[k] + y;
+                comp[k] = (t - sum[k]) - y;
+                sum[k] = t;
+                seen |= 1ull << k;
+            }
+        }
+    }
+    if (!live) return;
+    int best = -1;
+    for (int k = 0; k < n_spk; ++k)
+        if ((seen >> k) & 1ull)
+            if (best < 0 || sum[k] > sum[best]) best = k;      // descending sort, ties keep label order
+    out[q] = best;
+}
+
 }  // namespace wxb
 
 using namespace wxb;
@@ -1086,6 +1131,57 @@ extern "C" int wxb_plan_debug_trace(wxb_plan *pl, uint64_t *rows, int64_t cap_ro
         r[4] = d.T; r[5] = d.N; r[6] = d.K; r[7] = d.seg;
     }
     return n;
+}
+
+// ------------------------------------------------------------------ ABI: speaker assignment
+extern "C" int wxb_assign_speakers_device(wxb_ctx *ctx, const double *diar_start, const double *diar_end,
+                                          const int32_t *diar_speaker, int64_t n_diar, int32_t n_speakers,
+                                          const double *query_start, const double *query_end, int64_t n_query,
+                                          int32_t fill_nearest, int32_t *out_speaker, void *stream) {
+    if (!ctx) return fail(WXB_EINVAL, "wxb_assign_speakers: ctx is NULL");
+    if (n_diar < 0 || n_query < 0) return fail(WXB_EINVAL, "wxb_assign_speakers: negative count");
+    if (n_speakers < 0 || n_speakers > SPK_MAX) return fail(WXB_EUNSUPPORTED, "wxb_assign_speakers: %d speakers; at most %d are supported", n_speakers, SPK_MAX);
+    if (n_query == 0) return WXB_OK;
+    if (!query_start || !query_end || !out_speaker || (n_diar > 0 && (!diar_start || !diar_end || !diar_speaker)))
+        return fail(WXB_EINVAL, "wxb_assign_speakers: NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const long long blocks = (n_query + 127) / 128;
+    assign_speakers_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        diar_start, diar_end, diar_speaker, n_diar, n_speakers, query_start, query_end, n_query, fill_nearest, out_speaker);
+    CUDA_TRY(cudaGetLastError());
+    return WXB_OK;
+}
+
+extern "C" int wxb_assign_speakers_host(wxb_ctx *ctx, const double *diar_start, const double *diar_end,
+                                        const int32_t *diar_speaker, int64_t n_diar, int32_t n_speakers,
+                                        const double *query_start, const double *query_end, int64_t n_query,
+                                        int32_t fill_nearest, int32_t *out_speaker) {
+    if (!ctx) return fail(WXB_EINVAL, "wxb_assign_speakers: ctx is NULL");
+    if (n_diar < 0 || n_query < 0) return fail(WXB_EINVAL, "wxb_assign_speakers: negative count");
+    if (n_query == 0) return WXB_OK;
+    if (!query_start || !query_end || !out_speaker || (n_diar > 0 && (!diar_start || !diar_end || !diar_speaker)))
+        return fail(WXB_EINVAL, "wxb_assign_speakers: NULL argument");
+    for (int64_t i = 0; i < n_diar; ++i)
+        if (diar_speaker[i] < 0 || diar_speaker[i] >= n_speakers) return fail(WXB_EINVAL, "wxb_assign_speakers: diar_speaker[%lld]=%d outside [0,%d)", (long long)i, diar_speaker[i], n_speakers);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t nd = static_cast<size_t>(std::max<int64_t>(n_diar, 1)), nq = static_cast<size_t>(n_query);
+    CUDA_TRY(ctx->h_f64[0].ensure(nd * 8)); CUDA_TRY(ctx->h_f64[1].ensure(nd * 8)); CUDA_TRY(ctx->h_i32[0].ensure(nd * 4));
+    CUDA_TRY(ctx->h_f64[2].ensure(nq * 8)); CUDA_TRY(ctx->h_f64[3].ensure(nq * 8)); CUDA_TRY(ctx->h_i32[1].ensure(nq * 4));
+    cudaStream_t st = ctx->main;
+    if (n_diar > 0) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_f64[0].p, diar_start, nd * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_f64[1].p, diar_end, nd * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_i32[0].p, diar_speaker, nd * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_f64[2].p, query_start, nq * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_f64[3].p, query_end, nq * 8, cudaMemcpyHostToDevice, st));
+    int rc = wxb_assign_speakers_device(ctx, ctx->h_f64[0].as<double>(), ctx->h_f64[1].as<double>(), ctx->h_i32[0].as<int32_t>(), n_diar,
+                                        n_speakers, ctx->h_f64[2].as<double>(), ctx->h_f64[3].as<double>(), n_query, fill_nearest,
+                                        ctx->h_i32[1].as<int32_t>(), st);
+    if (rc != WXB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_speaker, ctx->h_i32[1].p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return WXB_OK;
 }
 
 // ------------------------------------------------------------------ ABI: stand-alone kernels
