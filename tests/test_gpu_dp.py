@@ -323,3 +323,33 @@ def test_backtrack_from_trellis_kernel(engine, golden_dp):
             on = np.nonzero(pt.numpy() >= 0)[0]
             assert on.tolist() == arr[n + "_ptime"].tolist() and pt.numpy()[on].tolist() == arr[n + "_ptok"].tolist()
             assert torch.exp(pl[on]).double().tolist() == arr[n + "_pscore"].tolist()
+
+
+def test_repeated_runs_are_bitwise_identical(engine):
+    """The wavefront hand-offs (mbarriers between producer and compute warps) must not leave room for a
+    race: the same plan run many times, interleaved with other plans, returns the same bytes."""
+    from whisperx_b200 import synth
+    b = synth.make_batch(384, "c2", align_frames=4, kind="planted")
+    spec = BatchSpec(frame_off=b.frame_off, frame_len=b.frame_len, tok_off=b.tok_off, tokens=b.tokens, vocab=b.vocab,
+                     blank_id=b.blank, logits=True, seg_t1=np.zeros(384), seg_ratio=b.durations / b.frame_len)
+    E = torch.from_numpy(b.emissions).cuda()
+    plan = engine.plan(spec)
+    other = synth.make_batch(64, "c4", align_frames=4)
+    ospec = BatchSpec(frame_off=other.frame_off, frame_len=other.frame_len, tok_off=other.tok_off, tokens=other.tokens,
+                      vocab=other.vocab, blank_id=other.blank, logits=True)
+    oE = torch.from_numpy(other.emissions).cuda()
+    first = None
+    for it in range(12):
+        res = plan.run(E, want=("path",))
+        if it % 3 == 1:
+            engine.align_batch(oE, ospec)           # a different shape class mix in between
+        torch.cuda.synchronize()
+        got = [getattr(res, f).cpu() for f in ("status", "n_frames", "char_start", "char_end", "char_score", "char_start_s",
+                                               "char_end_s", "char_score_r", "path_token", "path_logp")]
+        if first is None:
+            first = got
+            assert int(got[0].sum()) == 0
+        else:
+            for a, c in zip(first, got):
+                assert torch.equal(a.view(torch.uint8), c.view(torch.uint8))
+    plan.close()
