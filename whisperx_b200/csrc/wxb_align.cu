@@ -51,6 +51,81 @@ __global__ void __launch_bounds__(256) upload_kernel(uint4 *dst, const uint4 *sr
         dst[i] = src[i];
 }
 
+// ---- backtrack (:395-421) over the choice bits: one warp per segment, control flow warp-uniform ----
+// The walk needs one choice word per visited (column, 32-frame word) pair: ~N + T/32 *dependent*
+// loads if done naively.  Instead the warp fetches a window of 32 columns x 4 words (128 frames)
+// with 4 independent loads per lane and walks inside it on register shuffles; a new window is
+// fetched only when the path leaves the block: about max(N/32, T/128) dependent round trips per
+// segment.
+__global__ void __launch_bounds__(128) backtrack_kernel(const Params p, const int seg_first, const int count) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    const SegDesc db = p.segs[seg_first + idx];
+    const int K = db.K, W = db.W;
+    const int t_start = p.nframes[db.seg];
+    const int r = db.N - 32 * W * (K - 1);
+    const long long wstep = static_cast<long long>(W) * K * 32;
+    auto owner = [&](int k, int &g, int &slot) {     // token k -> global lane / register slot (see align_kernel)
+        if (K == 1 || k < r * K) { g = k / K; slot = k - g * K; }
+        else { const int kk = k - r * K; const int q = kk / (K - 1); g = r + q; slot = kk - q * (K - 1); }
+    };
+    int status = 0;
+    if (t_start == 0) {
+        status = 1;                                  // empty walk -> for/else -> None
+    } else {
+        int j = db.N;                                // current column (token j-1 is being located)
+        int s = t_start - 1;                         // frame of the current point
+        int *cs_ptr = p.c_start + db.tok_base + (j - 1);     // where token j-1's entry frame goes
+        bool more = true;
+        while (more) {
+            const int j0 = j;                        // window columns j0, j0-1, ..., j0-31
+            const int w0 = s >> 5;                   // window words   w0, w0-1, w0-2, w0-3
+            uint32_t wA = 0u, wB = 0u, wC = 0u, wD = 0u;
+            const int c = j0 - lane;
+            if (c >= 1) {
+                int g, slot;
+                owner(c - 1, g, slot);
+                const uint32_t *bp = p.bits + db.bits_off + static_cast<long long>(w0) * wstep + ((g >> 5) * K + slot) * 32 + (g & 31);
+                wA = __ldcg(bp);
+                if (w0 >= 1) wB = __ldcg(bp - 1 * wstep);
+                if (w0 >= 2) wC = __ldcg(bp - 2 * wstep);
+                if (w0 >= 3) wD = __ldcg(bp - 3 * wstep);
+            }
+            const int jmin = j0 - 31;                // leave the window below this column ...
+            const int smin = (w0 - 3) << 5;          // ... or below this frame
+            bool inside = true;
+            // One iteration per visited (column, word) pair, branch-free inside: either the token's
+            // entry frame is in this word (store it, move one column left) or the path stayed through
+            // the rest of the word (move to the previous word).
+            while (inside) {
+                const int dw = w0 - (s >> 5);        // 0..3 inside the window
+                const uint32_t lo = (dw & 1) ? wB : wA;
+                const uint32_t hi = (dw & 1) ? wD : wC;
+                const uint32_t mine = (dw & 2) ? hi : lo;
+                const uint32_t word = __shfl_sync(FULL, mine, j0 - j);
+                // bit (31 - f%32) is frame f; shift so that bit 0 = frame s, bit q = frame s-q
+                const uint32_t m = word >> (31 - (s & 31));
+                const bool found = (m != 0u);
+                const int sc = s - (__ffs(m) - 1);   // frame at which token j-1 was entered (if found)
+                if (found && lane == 0) *cs_ptr = sc;
+                cs_ptr -= found ? 1 : 0;
+                j -= found ? 1 : 0;
+                s = found ? sc - 1 : (s & ~31) - 1;
+                more = (j > 0) && (s >= 0);
+                inside = more && (j >= jmin) && (s >= smin);
+            }
+        }
+        status = (j == 0) ? 0 : 1;                   // ran out of frames before reaching token 0 -> None
+    }
+    if (lane == 0) {
+        p.status[db.seg] = status;
+        p.nframes[db.seg] = status ? 0 : t_start;
+        if (p.trace) p.trace[4ll * (seg_first + idx) + 2] = global_ns();
+    }
+    // merge_repeats, scores and timestamps run token-parallel in finalize_kernel
+}
+
 // ---- phase 3 as its own kernel: one thread per token of every segment ----
 // merge_repeats (:438-454): token k spans frames [start_k, start_{k+1}) (the last one ends at
 // t_start); its score is the mean of the path probabilities: exp(logp[start, token]) for the frame
@@ -811,7 +886,7 @@ extern "C" void wxb_plan_destroy(wxb_plan *plan) {
 extern "C" int wxb_plan_launch_count(const wxb_plan *plan) {
     if (!plan) return 0;
     int n = (plan->n_short > 0 ? 1 : 0) + (plan->has_words ? 1 : 0);
-    for (const Bucket &b : plan->buckets) n += 1 + (b.fin_count > 0 ? 1 : 0);      // align_kernel + its finalize_kernel
+    for (const Bucket &b : plan->buckets) n += 2 + (b.fin_count > 0 ? 1 : 0);      // align_kernel + backtrack_kernel + finalize_kernel
     return n;
 }
 
@@ -896,9 +971,10 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     CUDA_TRY(cudaStreamWaitEvent(st, pl->arena->uploaded, 0));     // the plan's metadata upload (ctx stream)
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t0, st));
     const int nb = static_cast<int>(pl->buckets.size());
-    // every class's finalize_kernel follows its align_kernel on the same stream, so it overlaps the
-    // other classes' recurrences instead of running after all of them
+    // every class's backtrack_kernel and finalize_kernel follow its align_kernel on the same stream, so
+    // they overlap the other classes' recurrences instead of running after all of them
     auto finalize = [&](const Bucket &b, cudaStream_t s) -> cudaError_t {
+        backtrack_kernel<<<(b.count + 3) / 4, 128, 0, s>>>(P, b.first, b.count);
         if (b.fin_count > 0) finalize_kernel<<<b.fin_count, 128, 0, s>>>(P, pl->d_fin + b.fin_first);
         return cudaGetLastError();
     };

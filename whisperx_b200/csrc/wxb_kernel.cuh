@@ -4,7 +4,7 @@
 // Replaces, for a whole batch of segments, the reference's per-segment Python:
 //   log_softmax            whisperx/alignment.py:233      (producer warp, fused into the tile staging)
 //   get_trellis            whisperx/alignment.py:359-379  (compute warps: recurrence, token axis in registers)
-//   backtrack              whisperx/alignment.py:387-421  (last compute warp: walk over packed choice bits)
+//   backtrack              whisperx/alignment.py:387-421  (backtrack_kernel in wxb_align.cu: walk over packed choice bits)
 //   merge_repeats          whisperx/alignment.py:438-454  (finalize_kernel: per-token start/end/mean prob)
 //   char timestamps        whisperx/alignment.py:252-264  (finalize_kernel: exact decimal rounding)
 //
@@ -474,73 +474,12 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
     if (wi != W) return;  // the producer warp holds the arg-max and walks back
     // best_val covers rows 0..T-1; row T wins only if strictly larger (first maximal index)
     if (T > 0 && *reinterpret_cast<const float *>(sm + L.off_fin) > best_val) t_start = T;
-    if (p.trace && lane == 0) p.trace[4ll * (seg_first + blockIdx.x) + 1] = global_ns();
-
-    // ---- backtrack (:395-421) over the choice bits; control flow is warp-uniform ----
-    // The walk needs one choice word per visited (column, 32-frame word) pair: ~N + T/32
-    // *dependent* loads if done naively.  Instead the warp fetches a window of 32 columns x 4 words
-    // (128 frames) with 4 independent loads per lane and walks inside it on register shuffles; a new
-    // window is fetched only when the path leaves the block: about max(N/32, T/128) dependent round
-    // trips per segment.
-    // (the descriptor is read again rather than kept live across the recurrence: registers there are
-    // worth more than one L2 hit here)
-    const SegDesc db = p.segs[seg_first + blockIdx.x];
-    const int r = db.N - 32 * W * (K - 1);
-    const long long wstep = static_cast<long long>(W) * K * 32;
-    int status = 0;
-    if (t_start == 0) {
-        status = 1;                                  // empty walk -> for/else -> None
-    } else {
-        int j = db.N;                                // current column (token j-1 is being located)
-        int s = t_start - 1;                         // frame of the current point
-        int *cs_ptr = p.c_start + db.tok_base + (j - 1);     // where token j-1's entry frame goes
-        bool more = true;
-        while (more) {
-            const int j0 = j;                        // window columns j0, j0-1, ..., j0-31
-            const int w0 = s >> 5;                   // window words   w0, w0-1, w0-2, w0-3
-            uint32_t wA = 0u, wB = 0u, wC = 0u, wD = 0u;
-            const int c = j0 - lane;
-            if (c >= 1) {
-                int g, slot;
-                owner_of<K>(c - 1, r, g, slot);
-                const uint32_t *bp = p.bits + db.bits_off + static_cast<long long>(w0) * wstep + ((g >> 5) * K + slot) * 32 + (g & 31);
-                wA = __ldcg(bp);
-                if (w0 >= 1) wB = __ldcg(bp - 1 * wstep);
-                if (w0 >= 2) wC = __ldcg(bp - 2 * wstep);
-                if (w0 >= 3) wD = __ldcg(bp - 3 * wstep);
-            }
-            const int jmin = j0 - 31;                // leave the window below this column ...
-            const int smin = (w0 - 3) << 5;          // ... or below this frame
-            bool inside = true;
-            // One iteration per visited (column, word) pair, branch-free inside: either the token's
-            // entry frame is in this word (store it, move one column left) or the path stayed through
-            // the rest of the word (move to the previous word).
-            while (inside) {
-                const int dw = w0 - (s >> 5);        // 0..3 inside the window
-                const uint32_t lo = (dw & 1) ? wB : wA;
-                const uint32_t hi = (dw & 1) ? wD : wC;
-                const uint32_t mine = (dw & 2) ? hi : lo;
-                const uint32_t word = __shfl_sync(FULL, mine, j0 - j);
-                // bit (31 - f%32) is frame f; shift so that bit 0 = frame s, bit q = frame s-q
-                const uint32_t m = word >> (31 - (s & 31));
-                const bool found = (m != 0u);
-                const int sc = s - (__ffs(m) - 1);   // frame at which token j-1 was entered (if found)
-                if (found && lane == 0) *cs_ptr = sc;
-                cs_ptr -= found ? 1 : 0;
-                j -= found ? 1 : 0;
-                s = found ? sc - 1 : (s & ~31) - 1;
-                more = (j > 0) && (s >= 0);
-                inside = more && (j >= jmin) && (s >= smin);
-            }
-        }
-        status = (j == 0) ? 0 : 1;                   // ran out of frames before reaching token 0 -> None
-    }
     if (lane == 0) {
-        p.status[db.seg] = status;
-        p.nframes[db.seg] = status ? 0 : t_start;
-        if (p.trace) p.trace[4ll * (seg_first + blockIdx.x) + 2] = global_ns();
+        p.nframes[d.seg] = t_start;            // arg-max of the last column; the walk starts here (backtrack_kernel)
+        if (p.trace) p.trace[4ll * (seg_first + blockIdx.x) + 1] = global_ns();
     }
-    // merge_repeats, scores and timestamps run token-parallel in finalize_kernel
+    // backtrack runs in backtrack_kernel (one warp per segment, no shared memory): the CTA gives its
+    // registers and shared memory back as soon as the forward pass is done
 }
 
 struct FinBlock { int desc; int k0; };   // finalize_kernel work item (see wxb_align.cu)
