@@ -42,6 +42,8 @@ extern "C" {
 /* flags for wxb_batch.flags */
 #define WXB_F_LOGITS        1u   /* emissions are raw logits: fuse log_softmax(dim=-1) (alignment.py:233) */
 #define WXB_F_NO_SHORTCUT   2u   /* run the DP even for N > T (tests); default marks them FAILED on the host */
+#define WXB_F_WILDCARD      4u   /* EXTENSION (not in the reference fork): token id -1 is a wildcard whose emission at
+                                    frame t is max over non-blank v of logp[t, v]; its path probability is exp of that */
 
 typedef struct wxb_ctx wxb_ctx;     /* per-device workspace (scratch buffers, side streams) */
 typedef struct wxb_plan wxb_plan;   /* a batch description uploaded and bucketed once, runnable many times */
@@ -59,7 +61,7 @@ typedef struct wxb_batch {
                                     are padding (e.g. segment starts rounded up to 4 rows so that every
                                     segment is 16-byte aligned and takes the bulk-copy path). */
     const int64_t *tok_off;      /* [S+1] ascending; N_s = tok_off[s+1]-tok_off[s] >= 0 */
-    const int32_t *tokens;       /* [tok_off[S]] values in [0, V) */
+    const int32_t *tokens;       /* [tok_off[S]] values in [0, V); -1 = wildcard with WXB_F_WILDCARD */
     /* Optional timestamp conversion (alignment.py:252-264): second = round(frame*ratio + t1, 3).
      * Both NULL -> the *_s / *_r / word outputs are not produced. */
     const double  *seg_t1;       /* [S] segment start time t1 (alignment.py:184) */

@@ -39,6 +39,16 @@ static inline float max_nan(float a, float b) {      /* torch.maximum */
     return a > b ? a : b;
 }
 
+/* emission[t, token] as the trellis and the backtrack read it.  EXTENSION (not in the reference fork,
+ * SURVEY Appendix C): token id -1 is a wildcard scored as the best non-blank symbol of the frame. */
+static inline float tok_emis(const float *e, int V, int tok, int blank) {
+    if (tok >= 0) return e[tok];
+    float m = -INFINITY;
+    for (int v = 0; v < V; ++v)
+        if (v != blank && e[v] > m) m = e[v];
+    return m;
+}
+
 /* get_trellis, alignment.py:359-379.  R is (T+1) x (N+1), row-major. */
 void wxo_forward_trellis(const float *E, int T, int V, const int32_t *tok, int N, int blank,
                          float *R) {
@@ -69,7 +79,7 @@ void wxo_forward_trellis(const float *E, int T, int V, const int32_t *tok, int N
         const float eb = e[blank];
         for (int j = 1; j <= N; ++j) {
             float stay = row[j] + eb;
-            float move = row[j - 1] + e[tok[j - 1]];
+            float move = row[j - 1] + tok_emis(e, V, tok[j - 1], blank);
             nxt[j] = max_nan(stay, move);
         }
     }
@@ -95,9 +105,9 @@ int wxo_walk_back(const float *R, const float *E, int T, int V, const int32_t *t
         if (j == 0) break;  /* unreachable for N>=1; guards N==0 like the empty loop would */
         const float *e = E + (size_t)(t - 1) * V;
         float stayed = R[(size_t)(t - 1) * W + j] + e[blank];
-        float changed = R[(size_t)(t - 1) * W + j - 1] + e[tok[j - 1]];
+        float changed = R[(size_t)(t - 1) * W + j - 1] + tok_emis(e, V, tok[j - 1], blank);
         int took = changed > stayed;
-        float lp = e[took ? tok[j - 1] : 0];        /* :409 literal column 0 on a stay */
+        float lp = took ? tok_emis(e, V, tok[j - 1], blank) : e[0];        /* :409 literal column 0 on a stay */
         p_tok[n] = j - 1;
         p_time[n] = t - 1;
         p_logp[n] = lp;

@@ -166,3 +166,38 @@ def test_functional_api_golden(wxa, golden_dp):
         words = wxa.merge_words(segs)
         assert [w.label for w in words] == m["words"] and [w.score for w in words] == a["wscore"].tolist()
         assert [w.start for w in words] == a["wstart"].tolist() and [w.end for w in words] == a["wend"].tolist()
+
+
+def test_wildcard_extension_end_to_end(wxa):
+    """EXTENSION (opt-in, not in the reference fork): with WILDCARD on, characters the model does not know
+    are aligned as wildcard tokens; compared with the oracle port's restatement of the same rule."""
+    rng = np.random.default_rng(33)
+    transcript = [
+        {"start": 0.0, "end": 4.0, "text": "It costs 2014 dollars & 50 cents."},
+        {"start": 4.0, "end": 6.5, "text": " 99 "},
+        {"start": 6.5, "end": 9.0, "text": "naïve café, 3 o'clock!"},
+    ]
+    audio = np.zeros(10 * 16000, np.float32)
+    logps = []
+    for seg in transcript:
+        T = (int(seg["end"] * 16000) - int(seg["start"] * 16000) - 400) // 320 + 1
+        logps.append(torch.log_softmax(torch.from_numpy(rng.standard_normal((T, len(LABELS))).astype(np.float32) * 3), -1))
+    meta = {"language": "en", "dictionary": DICTIONARY, "type": "torchaudio"}
+    wxa.EMISSION_MODE = "logprobs"
+    wxa.WILDCARD = True
+    try:
+        ours_in = copy.deepcopy(transcript)
+        ours = wxa.align(ours_in, ScriptedModel(logps, "cuda:0"), meta, audio, "cuda:0", return_char_alignments=True)
+    finally:
+        wxa.WILDCARD = False
+    ref_in = copy.deepcopy(transcript)
+    ref = ref_port.align_port(ref_in, ScriptedModel(logps), meta, audio, "cpu", return_char_alignments=True,
+                              span_fn=regex_spans, wildcard=True)
+    d = same_records(ours["segments"], ref["segments"], score_tol=0.0010001)
+    assert d is None, d
+    assert [s["clean_char"] for s in ours_in] == [s["clean_char"] for s in ref_in]
+    words = {w["word"]: w for w in ours["word_segments"]}
+    assert "start" in words["2014"] and "start" in words["&"] and "start" in words["99"]     # dropped by the reference fork
+    # off (default): identical to the reference behaviour — the digits get no timestamps
+    plain = wxa.align(copy.deepcopy(transcript), ScriptedModel(logps, "cuda:0"), meta, audio, "cuda:0")
+    assert "start" not in {w["word"]: w for w in plain["word_segments"]}["2014"]

@@ -358,3 +358,43 @@ def test_repeated_runs_are_bitwise_identical(engine):
             for a, c in zip(first, got):
                 assert torch.equal(a.view(torch.uint8), c.view(torch.uint8))
     plan.close()
+
+
+@pytest.mark.parametrize("V,blank", [(29, 0), (100, 99), (7, 3)])
+def test_wildcard_tokens_extension(engine, V, blank):
+    """EXTENSION (not in the reference fork; parity unpinned by the reference): token id -1 is
+    a wildcard whose emission is the best non-blank log-prob of the frame.  Checked against the oracle's
+    restatement of the same rule: trellis, path and frames bit-exact, scores 1e-6."""
+    from oracle import ref_port
+    rng = np.random.default_rng(500 + V)
+    cases = []
+    for N in (1, 3, 20, 33, 64, 100, 161, 257, 400, 700):
+        T = N + int(rng.integers(0, 200))
+        tok = rng.integers(0, V, N).astype(np.int32)
+        tok[rng.random(N) < 0.25] = -1
+        if N >= 3:
+            tok[0] = -1; tok[-1] = -1
+        cases.append((logprobs(rng, T, V, ties=bool(N % 2)), tok))
+    spec, res = run(engine, cases, V, blank, align=4, wildcard=True)
+    check_against_oracle(spec, res, cases, blank, full=True)
+    hopeless = [(logprobs(rng, 50, V), np.full(60, -1, np.int32))]           # N > T, all wildcards: fails
+    for no_shortcut in (False, True):
+        spec_h, res_h = run(engine, hopeless, V, blank, align=4, want=("path",), wildcard=True, no_shortcut=no_shortcut)
+        check_against_oracle(spec_h, res_h, hopeless, blank, full=False)
+        assert int(res_h.status[0]) == 1
+    # the two oracles agree with each other on the extension
+    E, tk = cases[3]
+    segs, _ = ref_port.align_tokens(torch.from_numpy(E), tk.tolist(), blank, "x" * len(tk))
+    rc, cs, ce, sc, _ = c_oracle.align_segment(E, tk, blank)
+    assert rc == 0 and [s.start for s in segs] == cs.tolist() and [s.end for s in segs] == ce.tolist()
+    np.testing.assert_allclose([s.score for s in segs], sc, rtol=SCORE_RTOL, atol=0)
+    # fused log-softmax + wildcards: path-exact on the engine's own log-probs
+    raw = [(rng.standard_normal((c[0].shape[0], V)).astype(np.float32) * 3, c[1]) for c in cases[:8]]
+    spec2, res2 = run(engine, raw, V, blank, align=4, want=("path", "logprobs"), wildcard=True, logits=True)
+    lp = res2.logprobs.view(-1, V)
+    own = [(lp[spec2.frame_off[s]:spec2.frame_off[s] + raw[s][0].shape[0]].numpy(), raw[s][1]) for s in range(len(raw))]
+    check_against_oracle(spec2, res2, own, blank, full=False)
+    # without the flag a -1 token is rejected
+    from whisperx_b200._native import NativeError
+    with pytest.raises(NativeError, match="outside"):
+        run(engine, cases[:2], V, blank)

@@ -68,6 +68,10 @@ EMISSION_MODE = os.environ.get("WXB_EMISSION_MODE", "fused")
 # >1: segments with the same number of samples share one wav2vec2 forward;
 # 1 keeps the reference's batch-1 forwards (alignment.py:215 has this as a TODO).
 EMISSION_BATCH = int(os.environ.get("WXB_EMISSION_BATCH", "1"))
+# EXTENSION, off by default (the reference fork drops characters its model does not know,
+# alignment.py:159-161): keep them as wildcard tokens scored as the best non-blank symbol of each
+# frame, so that digits, symbols and foreign letters get timestamps too.
+WILDCARD = os.environ.get("WXB_WILDCARD", "0") not in ("", "0")
 # Introspection for the parity tests: when True, align() keeps the last batch it ran (spec, device
 # results and, in fused mode, the log-probs the kernels computed) in LAST_BATCH.
 KEEP_LAST_BATCH = False
@@ -216,7 +220,7 @@ def align_grouped(transcript, model, align_model_metadata, audio, device, interp
 
     # 1. keep only characters the model knows (mutates the input, like the reference)
     transcript = transcript if isinstance(transcript, list) else list(transcript)
-    assemble.prepare_transcript(transcript, dictionary, lang, print_progress, combined_progress)
+    assemble.prepare_transcript(transcript, dictionary, lang, print_progress, combined_progress, wildcard=WILDCARD)
 
     # 2a. which segments reach the model (alignment.py:198-207)
     plain: List[dict] = []
@@ -283,7 +287,7 @@ def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], d
         T = int(logits[s].shape[0])
         frame_len[s] = T
         frame_off[s + 1] = frame_off[s] + T + (-T) % 4        # 4-row granules keep every segment 16-byte aligned
-        tokens += [dictionary[c] for c in seg["clean_char"]]
+        tokens += [dictionary.get(c, -1) for c in seg["clean_char"]]        # -1: wildcard entry (extension)
         tok_off[s + 1] = len(tokens)
         a, b = seg["start"], seg["end"]
         t1[s] = a
@@ -306,7 +310,8 @@ def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], d
         emis = torch.log_softmax(emis, dim=-1)
     has_words = len(wchar_off) > 1
     spec = BatchSpec(frame_off=frame_off, frame_len=frame_len, tok_off=tok_off, tokens=np.asarray(tokens, np.int32),
-                     vocab=V, blank_id=blank, logits=fused, seg_t1=t1, seg_ratio=ratio, seg_round_np=round_np,
+                     vocab=V, blank_id=blank, logits=fused, wildcard=(-1 in tokens), seg_t1=t1, seg_ratio=ratio,
+                     seg_round_np=round_np,
                      word_off=word_off if has_words else None,
                      wchar_off=np.asarray(wchar_off, np.int64) if has_words else None,
                      wchar_idx=np.asarray(wchar_idx, np.int32) if has_words else None)

@@ -85,10 +85,20 @@ def sentence_spans(text: str) -> list:
 
 
 # --------------------------------------------------------------------------- stage 1
+WILDCARD = "*"     # clean_char entry of a character the model does not know (wildcard extension only)
+
+
+def wildcard_symbol(dictionary: dict) -> str:
+    return WILDCARD if WILDCARD not in dictionary else "\0" + WILDCARD
+
+
 def prepare_transcript(transcript, dictionary: dict, lang: str, print_progress: bool = False,
-                       combined_progress: bool = False) -> None:
+                       combined_progress: bool = False, wildcard: bool = False) -> None:
     """align() stage 1 (alignment.py:128-177): adds clean_char / clean_cdx / clean_wdx /
-    sentence_spans to every input segment dict (the reference mutates its input the same way)."""
+    sentence_spans to every input segment dict (the reference mutates its input the same way).
+    `wildcard` (extension, off by default): characters the model does not know are kept as wildcard
+    entries instead of being dropped, so that e.g. digits receive timestamps too."""
+    wild = wildcard_symbol(dictionary)
     spaced = lang not in LANGUAGES_WITHOUT_SPACES
     total = len(transcript)
     for sdx, seg in enumerate(transcript):
@@ -106,10 +116,13 @@ def prepare_transcript(transcript, dictionary: dict, lang: str, print_progress: 
             if c in dictionary:
                 chars.append(c)
                 cdx.append(i)
+            elif wildcard:
+                chars.append(wild)
+                cdx.append(i)
         units = text.split(" ") if spaced else text
         seg["clean_char"] = chars
         seg["clean_cdx"] = cdx
-        seg["clean_wdx"] = [k for k, w in enumerate(units) if any(c in dictionary for c in w)]
+        seg["clean_wdx"] = [k for k, w in enumerate(units) if (len(w) > 0 if wildcard else any(c in dictionary for c in w))]
         seg["sentence_spans"] = sentence_spans(text)
 
 

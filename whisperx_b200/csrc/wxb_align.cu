@@ -16,7 +16,7 @@
 #include <vector>
 
 namespace wxb {
-cudaError_t launch_align(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug);
+cudaError_t launch_align(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug, bool wild);
 
 constexpr int NSIDE = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -158,9 +158,14 @@ __global__ void __launch_bounds__(128) finalize_kernel(const Params p, const Fin
     const float *Eg = p.emis + d.emis_off;
     const int sf = p.c_start[o];
     const int ef = (k == N - 1) ? t_start : p.c_start[o + 1];
-    const int tk = __ldg(p.tok4 + o) >> 2;
-    float x = __ldg(Eg + static_cast<size_t>(sf) * V + tk);
-    if (p.is_logits) x = logp_from(x, p.rowmax[d.frame_base + sf], p.rowlse[d.frame_base + sf]);
+    const int t4 = __ldg(p.tok4 + o);
+    float x;
+    if (t4 < 0) {
+        x = p.wild[d.frame_base + sf];                    // wildcard token: max over the non-blank vocabulary (a log-prob already)
+    } else {
+        x = __ldg(Eg + static_cast<size_t>(sf) * V + (t4 >> 2));
+        if (p.is_logits) x = logp_from(x, p.rowmax[d.frame_base + sf], p.rowlse[d.frame_base + sf]);
+    }
     double sum = static_cast<double>(expf(x));           // Python sum(): 0 + p_first + ...
     for (int f = sf + 1; f < ef; ++f) sum += static_cast<double>(p.p0[d.frame_base + f]);
     const double score = sum / static_cast<double>(ef - sf);
@@ -431,7 +436,7 @@ struct wxb_ctx {
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<cudaEvent_t> ev_chunk;        // one per emission chunk in flight
-    DevBuf bits, p0, rowmax, rowlse, nframes_scratch, trace;
+    DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, trace;
     int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
     bool want_trace = false;                  // WXB_TRACE=1
     size_t chunk_bytes = 64u << 20;           // WXB_CHUNK_MB: emission bytes per pipelined H2D chunk
@@ -447,7 +452,7 @@ struct wxb_plan {
     int64_t S = 0, W = 0, sum_T = 0, sum_N = 0;
     int V = 0, blank = 0;
     uint32_t flags = 0;
-    bool has_sec = false, has_words = false, has_round_np = false;
+    bool has_sec = false, has_words = false, has_round_np = false, has_wild = false;
     std::vector<Bucket> buckets;              // chunk-major, longest segments first inside a chunk
     std::vector<int64_t> chunk_row;           // [n_chunks+1] emission row range of each chunk
     std::vector<int64_t> chunk_seg;           // [n_chunks+1] input-segment range whose last row lies in each chunk
@@ -516,21 +521,21 @@ static int g_tile_pref = 32;     // WXB_TILE_FRAMES (experiments): largest tile 
 // with many warps); the ring is W+2 deep — every warp on its own tile plus one being filled — or
 // shallower if shared memory says so (any depth >= 2 is deadlock-free).  cp.async.bulk needs
 // 16-byte multiples, i.e. TE % 4 == 0.
-static int pick_shape(int W, int V, int *TE, int *NB, size_t *smem) {
+static int pick_shape(int W, int V, int entry, int *TE, int *NB, size_t *smem) {
     const int pref[4] = {32, 16, 8, 4};
     const int want_ctas = std::max(1, (16 + W) / (W + 1));
     int chosen = -1;
     for (int i = 0; i < 4 && chosen < 0; ++i) {
         if (pref[i] > g_tile_pref) continue;
-        if (smem_layout(W, W + 2, pref[i], V).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+        if (smem_layout(W, W + 2, pref[i], V, entry).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     }
     for (int i = 0; i < 4 && chosen < 0; ++i)         // nothing reaches the occupancy target: the longest tile that fits at all
-        if (pref[i] <= g_tile_pref && smem_layout(W, 2, pref[i], V).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+        if (pref[i] <= g_tile_pref && smem_layout(W, 2, pref[i], V, entry).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     if (chosen < 0) return -1;
     int nb = W + 2;
-    while (nb > 2 && smem_layout(W, nb, chosen, V).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
+    while (nb > 2 && smem_layout(W, nb, chosen, V, entry).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
     *TE = chosen; *NB = nb;
-    *smem = smem_layout(W, nb, chosen, V).total;
+    *smem = smem_layout(W, nb, chosen, V, entry).total;
     return 0;
 }
 
@@ -597,7 +602,7 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->nframes_scratch, &c->h_emis, &c->h_path_tok};
+    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->wild, &c->nframes_scratch, &c->h_emis, &c->h_path_tok};
     for (DevBuf *b : bufs) b->release();
     for (auto &b : c->h_i32) b.release();
     for (auto &b : c->h_f64) b.release();
@@ -666,6 +671,8 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     pl->has_sec = bt->seg_t1 != nullptr;
     pl->W = bt->n_words;
     pl->has_words = bt->n_words > 0;
+    pl->has_wild = (bt->flags & WXB_F_WILDCARD) != 0;
+    const int entry = pl->has_wild ? 16 : 8;            // bytes per boundary entry in shared memory (see align_kernel)
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (S == 0) { guard.p = nullptr; *out = pl; return WXB_OK; }
 
@@ -738,7 +745,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     pl->n_short = static_cast<int>(shorts.size());
     {
         int te, nbq; size_t sm;
-        if (pick_shape(wmax, pl->V, &te, &nbq, &sm) != 0)
+        if (pick_shape(wmax, pl->V, entry, &te, &nbq, &sm) != 0)
             return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory for a %d-warp segment", pl->V, SMEM_LIMIT, wmax);
     }
     // one launch per (chunk, warps, tokens-per-lane) class; longest-first inside a class: the block
@@ -756,7 +763,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].W * descs[i].K * 32;
         if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W || descs[i].pad != descs[i - 1].pad) {
             Bucket b{descs[i].K, descs[i].W, 0, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad, fin_next, 0};
-            pick_shape(b.W, pl->V, &b.TE, &b.NB, &b.smem);
+            pick_shape(b.W, pl->V, entry, &b.TE, &b.NB, &b.smem);
             pl->buckets.push_back(b);
         }
         pl->buckets.back().count += 1;
@@ -814,14 +821,15 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         int *tok4 = reinterpret_cast<int *>(h + o_tok4);
         const int32_t *tk = bt->tokens;
         const uint32_t V = static_cast<uint32_t>(pl->V);
+        const uint32_t lo = pl->has_wild ? 1u : 0u;          // with wildcards, id -1 is legal: check tk + 1 in [0, V + 1)
         uint32_t bad = 0;
         for (size_t i = 0; i < sN; ++i) {
-            bad |= (static_cast<uint32_t>(tk[i]) >= V);       // negative ids wrap to large unsigned values
-            tok4[i] = tk[i] * 4;
+            bad |= (static_cast<uint32_t>(tk[i]) + lo >= V + lo);   // other negative ids wrap to large unsigned values
+            tok4[i] = tk[i] * 4;                                     // wildcard -> -4: "no row offset"
         }
         if (bad)
             for (size_t i = 0; i < sN; ++i)
-                if (tk[i] < 0 || tk[i] >= pl->V) return fail(WXB_EINVAL, "wxb_plan_create: tokens[%lld]=%d outside [0,%d)", (long long)i, tk[i], pl->V);
+                if (tk[i] < -static_cast<int>(lo) || tk[i] >= pl->V) return fail(WXB_EINVAL, "wxb_plan_create: tokens[%lld]=%d outside [%d,%d)", (long long)i, tk[i], -static_cast<int>(lo), pl->V);
     }
     if (!shorts.empty()) memcpy(h + o_short, shorts.data(), shorts.size() * sizeof(ShortSeg));
     if (pl->has_sec) {
@@ -932,6 +940,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(c->bits.ensure(static_cast<size_t>(std::max<long long>(pl->bits_words, 1)) * 4));
     CUDA_TRY(c->p0.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+    if (pl->has_wild) CUDA_TRY(c->wild.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
     if (logits) {
         CUDA_TRY(c->rowmax.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
         CUDA_TRY(c->rowlse.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
@@ -951,6 +960,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     P.p0 = c->p0.as<float>();
     P.rowmax = c->rowmax.as<float>();
     P.rowlse = c->rowlse.as<float>();
+    P.wild = c->wild.as<float>();
     P.V = pl->V; P.blank = pl->blank; P.is_logits = logits ? 1 : 0;
     P.status = o->status; P.nframes = nframes;
     P.c_start = o->char_start; P.c_end = o->char_end; P.c_score = o->char_score;
@@ -995,7 +1005,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     };
     if (nb == 1 && !chunk_ready) {
         const Bucket &b = pl->buckets[0];
-        CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, st, debug));
+        CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, st, debug, pl->has_wild));
         CUDA_TRY(finalize(b, st));
     } else if (nb >= 1) {
         // classes are independent: fork onto side streams so that every SM sees a mix of them
@@ -1041,7 +1051,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
                 CUDA_TRY(cudaStreamWaitEvent(c->side[si], chunk_ready[b.chunk], 0));
                 seen_chunk[si] = b.chunk;
             }
-            CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, c->side[si], debug));
+            CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, c->side[si], debug, pl->has_wild));
             CUDA_TRY(finalize(b, c->side[si]));
         }
         if (sink) {

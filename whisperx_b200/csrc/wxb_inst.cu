@@ -1,4 +1,4 @@
-// Instantiates align_kernel<K, DEBUG> for K = 1..KMAX and dispatches a launch to the right one.
+// Instantiates align_kernel<K, DEBUG, WILD> for K = 1..KMAX and dispatches a launch to the right one.
 #include "wxb_kernel.cuh"
 
 #include <algorithm>
@@ -7,7 +7,7 @@
 
 namespace wxb {
 
-template <int K, bool DEBUG>
+template <int K, bool DEBUG, bool WILD>
 static cudaError_t configure(size_t smem) {
     // Every instantiation asks for the maximum shared-memory carveout: kernels that want different
     // L1/shared splits cannot be co-resident on an SM, and a plan runs one launch per
@@ -15,11 +15,11 @@ static cudaError_t configure(size_t smem) {
     static size_t configured_for = 0;
     static bool first = true;
     if (!first && smem <= configured_for) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(align_kernel<K, DEBUG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaError_t e = cudaFuncSetAttribute(align_kernel<K, DEBUG, WILD>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(align_kernel<K, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(align_kernel<K, DEBUG, WILD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         configured_for = 227 * 1024;
     } else {
@@ -29,33 +29,41 @@ static cudaError_t configure(size_t smem) {
     return cudaSuccess;
 }
 
-template <int K>
-static cudaError_t launch_one(int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
-    cudaError_t e = debug ? configure<K, true>(smem) : configure<K, false>(smem);
+template <int K, bool DEBUG, bool WILD>
+static cudaError_t launch_variant(int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st) {
+    cudaError_t e = configure<K, DEBUG, WILD>(smem);
     if (e != cudaSuccess) return e;
     const int threads = 32 * (warps + 1);            // + the producer warp
     if (getenv("WXB_DEBUG_OCC")) {
         int nbk = 0;
         cudaFuncAttributes fa;
-        if (debug) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, align_kernel<K, true>, threads, smem); cudaFuncGetAttributes(&fa, align_kernel<K, true>); }
-        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, align_kernel<K, false>, threads, smem); cudaFuncGetAttributes(&fa, align_kernel<K, false>); }
-        fprintf(stderr, "[wxb] align_kernel<%d,%d> W=%d NB=%d TE=%d: regs=%d smem=%zu grid=%d -> %d CTAs/SM\n", K, (int)debug, warps, nb, te, fa.numRegs, smem, count, nbk);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, align_kernel<K, DEBUG, WILD>, threads, smem);
+        cudaFuncGetAttributes(&fa, align_kernel<K, DEBUG, WILD>);
+        fprintf(stderr, "[wxb] align_kernel<%d,%d,%d> W=%d NB=%d TE=%d: regs=%d smem=%zu grid=%d -> %d CTAs/SM\n", K, (int)DEBUG, (int)WILD,
+                warps, nb, te, fa.numRegs, smem, count, nbk);
     }
-    if (debug) align_kernel<K, true><<<count, threads, smem, st>>>(p, first, nb, te);
-    else       align_kernel<K, false><<<count, threads, smem, st>>>(p, first, nb, te);
+    align_kernel<K, DEBUG, WILD><<<count, threads, smem, st>>>(p, first, nb, te);
     return cudaGetLastError();
 }
 
 template <int K>
-static cudaError_t dispatch(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
-    if (k == K) return launch_one<K>(warps, nb, te, p, first, count, smem, st, debug);
-    if constexpr (K < KMAX) return dispatch<K + 1>(k, warps, nb, te, p, first, count, smem, st, debug);
+static cudaError_t launch_one(int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug, bool wild) {
+    if (debug) return wild ? launch_variant<K, true, true>(warps, nb, te, p, first, count, smem, st)
+                           : launch_variant<K, true, false>(warps, nb, te, p, first, count, smem, st);
+    return wild ? launch_variant<K, false, true>(warps, nb, te, p, first, count, smem, st)
+                : launch_variant<K, false, false>(warps, nb, te, p, first, count, smem, st);
+}
+
+template <int K>
+static cudaError_t dispatch(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug, bool wild) {
+    if (k == K) return launch_one<K>(warps, nb, te, p, first, count, smem, st, debug, wild);
+    if constexpr (K < KMAX) return dispatch<K + 1>(k, warps, nb, te, p, first, count, smem, st, debug, wild);
     else return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_align(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug) {
+cudaError_t launch_align(int k, int warps, int nb, int te, const Params &p, int first, int count, size_t smem, cudaStream_t st, bool debug, bool wild) {
     if (warps < 1 || warps > WMAX || nb < 2) return cudaErrorInvalidValue;
-    return dispatch<1>(k, warps, nb, te, p, first, count, smem, st, debug);
+    return dispatch<1>(k, warps, nb, te, p, first, count, smem, st, debug, wild);
 }
 
 }  // namespace wxb

@@ -51,6 +51,7 @@ struct Params {
     const SegDesc *segs;
     uint32_t *bits;         // choice words of a segment: word ((t/32)*W*K + w*K + slot)*32 + lane, bit 31-(t%32)
     float *p0;              // [sum_T] expf(logp[t, 0])
+    float *wild;            // [sum_T] (wildcard batches) max over non-blank v of logp[t, v]
     float *rowmax;          // [sum_T] (logits mode) row max
     float *rowlse;          // [sum_T] (logits mode) log(sum(exp(x - max)))
     int V, blank, is_logits, pad0;
@@ -75,11 +76,11 @@ constexpr int WMAX = 31;         // compute warps per CTA (+1 producer warp = 10
 struct SmemLayout {
     uint32_t tile_bytes, off_left, off_xd, off_fin, off_bar, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int W, int NB, int TE, int V) {
+__host__ __device__ inline SmemLayout smem_layout(int W, int NB, int TE, int V, int entry_bytes = 8) {
     SmemLayout L;
     L.tile_bytes = static_cast<uint32_t>(TE) * V * 4u;                    // TE % 4 == 0 -> multiple of 16
-    L.off_left = static_cast<uint32_t>(NB) * L.tile_bytes;                // left[W+1][NB][TE] float2 {boundary, blank}
-    L.off_xd = (L.off_left + static_cast<uint32_t>(W + 1) * NB * TE * 8u + 15u) & ~15u;   // 32 doubles
+    L.off_left = static_cast<uint32_t>(NB) * L.tile_bytes;                // left[W+1][NB][TE] {boundary, blank} (+ {wildcard, -})
+    L.off_xd = (L.off_left + static_cast<uint32_t>(W + 1) * NB * TE * static_cast<uint32_t>(entry_bytes) + 15u) & ~15u;   // 32 doubles
     L.off_fin = L.off_xd + 256u;                                          // trellis[T, N] (one float)
     L.off_bar = L.off_fin + 16u;                                          // tma[NB] full[NB] empty[NB] edge[W][NB]
     L.total = L.off_bar + static_cast<uint32_t>(3 + W) * NB * 8u;
@@ -106,6 +107,14 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f32x2(uint32_t addr, float a, float b) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32x4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // torch.maximum: NaN-propagating max in one FMNMX.NAN
 __device__ __forceinline__ float fmax_nan(float a, float b) {
@@ -156,8 +165,12 @@ __device__ __forceinline__ void owner_of(int k, int r, int &g, int &slot) {
 #define WXB_REGS(K) ((K) <= 4 ? 40 : (K) <= 6 ? 56 : 64)
 #endif
 
-template <int K, bool DEBUG>
-__global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params p, const int seg_first, const int NB, const int TE) {
+// WILD: the batch contains wildcard tokens (id -1, an extension over the reference — see DESIGN.md):
+// their emission at frame t is max over non-blank v of logp[t, v]; the producer computes it per frame
+// and it travels with the boundary entries ({boundary, blank, wildcard, -} instead of {boundary, blank}).
+template <int K, bool DEBUG, bool WILD>
+__global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(const Params p, const int seg_first, const int NB, const int TE) {
+    constexpr uint32_t EB = WILD ? 16u : 8u;        // bytes per boundary entry
     extern __shared__ __align__(128) unsigned char sm[];
     const int lane = threadIdx.x & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform (uniform registers for the
@@ -172,13 +185,13 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
         p.trace[4ll * (seg_first + blockIdx.x) + 0] = global_ns();
         p.trace[4ll * (seg_first + blockIdx.x) + 3] = smid;
     }
-    const SmemLayout L = smem_layout(W, NB, TE, V);
+    const SmemLayout L = smem_layout(W, NB, TE, V, EB);
     const uint32_t sm_base = smem_u32(sm);
     const uint32_t bar_tma = sm_base + L.off_bar;
     const uint32_t bar_full = bar_tma + 8u * NB;
     const uint32_t bar_empty = bar_full + 8u * NB;
     const uint32_t bar_edge = bar_empty + 8u * NB;     // [w][b], w = 0..W-1 (row 0 unused)
-    const uint32_t left_stride_w = static_cast<uint32_t>(NB) * TE * 8u;   // bytes between left[w] and left[w+1]
+    const uint32_t left_stride_w = static_cast<uint32_t>(NB) * TE * EB;   // bytes between left[w] and left[w+1]
     const int ntiles = (T + TE - 1) / TE;
     const float *Eg = p.emis + d.emis_off;
 
@@ -219,8 +232,8 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
         uint32_t sph = 0;
         auto scan_next = [&]() {
             mbar_wait(bar_empty + 8u * sb, sph);
-            const float2 *fin = reinterpret_cast<const float2 *>(sm + L.off_left) + (W * NB + sb) * TE;
-            float v = (st0 + lane < T && lane < TE) ? fin[lane].x : -INFINITY;
+            const unsigned char *fin = sm + L.off_left + static_cast<uint32_t>((W * NB + sb) * TE) * EB;
+            float v = (st0 + lane < T && lane < TE) ? *reinterpret_cast<const float *>(fin + lane * EB) : -INFINITY;
             int vi = st0 + lane;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -295,7 +308,7 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
                 }
             }
             // ---- column 0 of the trellis for rows t0 .. t0+n-1 (exclusive float64 prefix) ----
-            float2 *col0 = reinterpret_cast<float2 *>(sm + L.off_left) + b * TE;   // left[0][b][:] = {trellis[t, 0], logp[t, blank]}
+            unsigned char *col0 = sm + L.off_left + static_cast<uint32_t>(b * TE) * EB;   // left[0][b][:] = {trellis[t, 0], logp[t, blank](, wildcard)}
             const float e0 = (lane < n) ? tb[lane * V] : 0.0f;
             if (lane < n) p.p0[d.frame_base + t0 + lane] = expf(e0);
             float mine_f = INFINITY;
@@ -310,7 +323,18 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
                 __syncwarp();
                 if (t0 + lane < infstart) mine_f = static_cast<float>(mine);
             }
-            if (lane < n) col0[lane] = make_float2(mine_f, tb[lane * V + p.blank]);
+            if (lane < n) {
+                const float ebl = tb[lane * V + p.blank];
+                if (WILD) {
+                    float wv = -INFINITY;           // max over the non-blank vocabulary
+                    for (int v = 0; v < V; ++v)
+                        if (v != p.blank) wv = fmaxf(wv, tb[lane * V + v]);
+                    p.wild[d.frame_base + t0 + lane] = wv;
+                    *reinterpret_cast<float4 *>(col0 + lane * EB) = make_float4(mine_f, ebl, wv, 0.0f);
+                } else {
+                    *reinterpret_cast<float2 *>(col0 + lane * EB) = make_float2(mine_f, ebl);
+                }
+            }
             if (DEBUG) {
                 float *tr = p.trellis + d.trellis_off;
                 if (lane < n) tr[static_cast<long long>(t0 + lane) * (N + 1)] = mine_f;
@@ -336,10 +360,13 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
         const int laneN = (K == 1 && last_warp) ? (N - 1 - 32 * (W - 1)) : 31;
 
         uint32_t tokoff[K];
+        uint32_t wmask = 0u;            // (WILD) bit i: column i is a wildcard token
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             // byte offsets (token*4) come pre-multiplied from the plan: LDS [R + UR] with a uniform row base
-            tokoff[i] = (i < ncols) ? static_cast<uint32_t>(__ldg(p.tok4 + d.tok_base + cb + i)) : 0u;
+            const int t4 = (i < ncols) ? __ldg(p.tok4 + d.tok_base + cb + i) : 0;
+            if (WILD && t4 < 0) wmask |= 1u << i;
+            tokoff[i] = (t4 < 0) ? 0u : static_cast<uint32_t>(t4);
         }
         float R[K];
         uint32_t acc[K];
@@ -370,7 +397,7 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
             ph ^= wrap ? 1u : 0u;
             const int n = min(TE, T - tau * TE);
             mbar_wait(wait_bar0 + 8u * b, ph);
-            if (lane < n) sts_f32x2(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * 8u, -INFINITY, 0.0f);
+            if (lane < n) sts_f32x2(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * EB, -INFINITY, 0.0f);
             if (n == 32) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) bits_w[i * 32] = 0u;
@@ -391,23 +418,29 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
             mbar_wait(wait_bar0 + 8u * b, ph);
 
             uint32_t rowaddr = sm_base + b * L.tile_bytes;
-            uint32_t left_in = left_in0 + static_cast<uint32_t>(b * TE) * 8u;     // + 8*tt as the tile advances
+            uint32_t left_in = left_in0 + static_cast<uint32_t>(b * TE) * EB;     // + EB*tt as the tile advances
             uint32_t left_out = left_in + left_stride_w;
             asm volatile("" : "+r"(left_in), "+r"(left_out));   // materialise once per tile, not per frame under a predicate
 
             // ---- the recurrence (:372-378) ----
             auto step = [&](int u) {         // u = frame inside the current unrolled block (a literal after unrolling)
-                const float2 lv = lds_f32x2(left_in + 8u * u);        // {trellis[t, my first column - 1], logp[t, blank]}
+                float4 lv;                                             // {trellis[t, my first column - 1], logp[t, blank](, wildcard)}
+                if (WILD) lv = lds_f32x4(left_in + EB * u);
+                else { const float2 l2 = lds_f32x2(left_in + EB * u); lv = make_float4(l2.x, l2.y, 0.0f, 0.0f); }
                 const float eb = lv.y;
                 float left = __shfl_up_sync(FULL, src, 1);
                 if (lane == 0) left = lv.x;
-                if (lane == laneN) sts_f32x2(left_out + 8u * u, src, eb);   // row t of my last column -> warp wi+1
+                if (lane == laneN) {                                   // row t of my last column -> warp wi+1
+                    if (WILD) sts_f32x4(left_out + EB * u, src, eb, lv.z, 0.0f);
+                    else sts_f32x2(left_out + EB * u, src, eb);
+                }
                 // chg first (it reads the *old* left neighbours), then stay / sign-difference as packed
                 // f32x2 adds (FADD2 on sm_100: one issue slot for two cells; IEEE round-to-nearest per lane)
                 float chg[K];
 #pragma unroll
                 for (int i = K - 1; i >= 0; --i) {
-                    const float e = lds_f32(rowaddr + tokoff[i]);
+                    float e = lds_f32(rowaddr + tokoff[i]);
+                    if (WILD && ((wmask >> i) & 1u)) e = lv.z;
                     chg[i] = ((i == 0) ? left : R[i - 1]) + e;    // trellis[t, j-1] + emission[t, tokens[j-1]]
                 }
 #pragma unroll
@@ -449,14 +482,14 @@ __global__ void __maxnreg__(DEBUG ? 64 : WXB_REGS(K)) align_kernel(const Params 
             for (; tt + WXB_UNROLL <= n; tt += WXB_UNROLL) {
 #pragma unroll
                 for (int u = 0; u < WXB_UNROLL; ++u) step(u);
-                left_in += 8u * WXB_UNROLL;
-                left_out += 8u * WXB_UNROLL;
+                left_in += EB * WXB_UNROLL;
+                left_out += EB * WXB_UNROLL;
                 flush_if_word_done();
             }
             for (; tt < n; ++tt) {
                 step(0);
-                left_in += 8u;
-                left_out += 8u;
+                left_in += EB;
+                left_out += EB;
                 flush_if_word_done();
             }
             __syncwarp();
