@@ -388,7 +388,7 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
         // tiles below that frame are passed on without running the recurrence.
         const int g0 = wi * 32;
         const int col0w = (g0 < r) ? g0 * K : r * K + (g0 - r) * (K - 1);
-        const int skip_tiles = (!DEBUG && TE == 32) ? min(col0w >> 5, ntiles) : 0;
+        const int skip_tiles = DEBUG ? 0 : min(col0w / TE, ntiles);
         int tau = 0;
         for (; tau < skip_tiles; ++tau) {
             ++b;
@@ -398,12 +398,12 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             const int n = min(TE, T - tau * TE);
             mbar_wait(wait_bar0 + 8u * b, ph);
             if (lane < n) sts_f32x2(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * EB, -INFINITY, 0.0f);
-            if (n == 32) {
+            t += n;
+            if ((t & 31) == 0) {            // a 32-frame choice word is complete: all zeros
 #pragma unroll
                 for (int i = 0; i < K; ++i) bits_w[i * 32] = 0u;
                 bits_w += bits_step;
             }
-            t += n;
             __syncwarp();
             if (lane == 0) mbar_arrive(next_bar0 + 8u * b);
         }
