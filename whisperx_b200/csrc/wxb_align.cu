@@ -519,6 +519,7 @@ static int tokens_per_lane(long long n) {
 // Frames per shared-memory tile (cp.async.bulk needs 16-byte multiples, i.e. TE % 4 == 0): 32 when the
 // widest CTA of the batch still fits a ring of at least 2 tiles, else 16, 8, 4.
 static int g_tile_pref = 32;     // WXB_TILE_FRAMES (experiments): largest tile length tried
+static int g_ring_extra = 2;     // WXB_RING_EXTRA (experiments): ring depth = W + this
 
 // Tile length (frames) and ring depth of a W-warp CTA over a V-wide vocabulary.  32-frame tiles
 // amortise the per-tile hand-offs best (measured: 16 costs +25 % on the V=29 benchmark), so they are
@@ -532,12 +533,12 @@ static int pick_shape(int W, int V, int entry, int *TE, int *NB, size_t *smem) {
     int chosen = -1;
     for (int i = 0; i < 4 && chosen < 0; ++i) {
         if (pref[i] > g_tile_pref) continue;
-        if (smem_layout(W, W + 2, pref[i], V, entry).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+        if (smem_layout(W, W + g_ring_extra, pref[i], V, entry).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     }
     for (int i = 0; i < 4 && chosen < 0; ++i)         // nothing reaches the occupancy target: the longest tile that fits at all
         if (pref[i] <= g_tile_pref && smem_layout(W, 2, pref[i], V, entry).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     if (chosen < 0) return -1;
-    int nb = W + 2;
+    int nb = std::max(2, W + g_ring_extra);
     while (nb > 2 && smem_layout(W, nb, chosen, V, entry).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
     *TE = chosen; *NB = nb;
     *smem = smem_layout(W, nb, chosen, V, entry).total;
@@ -583,6 +584,7 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     if (const char *e = getenv("WXB_TRACE")) c->want_trace = atoi(e) != 0;
     if (const char *e = getenv("WXB_K_TARGET")) g_k_target = std::max(1, std::min(KMAX, atoi(e)));
     if (const char *e = getenv("WXB_TILE_FRAMES")) g_tile_pref = std::max(4, std::min(32, atoi(e)));
+    if (const char *e = getenv("WXB_RING_EXTRA")) g_ring_extra = std::max(1, std::min(4, atoi(e)));
     if (const char *e = getenv("WXB_CHUNK_MB")) c->chunk_bytes = static_cast<size_t>(std::max(1, atoi(e))) << 20;
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
