@@ -134,7 +134,8 @@ int  wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg_bytes, in
  * non-NULL `out` pointers are DEVICE memory; work is enqueued on `stream` (a cudaStream_t cast
  * to void*; NULL = legacy default stream) and the call returns without synchronising.
  * `elapsed_dp_ms`, if not NULL, makes the call synchronise and report the CUDA-event time of
- * the DP kernels alone. */
+ * the DP kernels alone.  Calls that repeat the same (emissions, outputs) pointers are replayed as a
+ * CUDA graph from the third one on (WXB_GRAPHS=0 disables). */
 int  wxb_plan_run(wxb_plan *plan, const float *emissions_dev, const wxb_outputs *out_dev,
                   void *stream, float *elapsed_dp_ms);
 

@@ -357,6 +357,26 @@ def test_repeated_runs_are_bitwise_identical(engine):
         else:
             for a, c in zip(first, got):
                 assert torch.equal(a.view(torch.uint8), c.view(torch.uint8))
+    # same buffers every call: from the third call on the plan is replayed as a CUDA graph; a larger plan in
+    # between regrows the context's scratch, which must invalidate the captured pointers
+    from whisperx_b200.engine import _alloc_outputs
+    out = _alloc_outputs(spec, engine.device, ("path",))
+    big = synth.make_batch(700, "c5", align_frames=4)
+    bspec = BatchSpec(frame_off=big.frame_off, frame_len=big.frame_len, tok_off=big.tok_off, tokens=big.tokens,
+                      vocab=big.vocab, blank_id=big.blank, logits=True)
+    bE = torch.from_numpy(big.emissions).cuda()
+    for it in range(10):
+        for f in ("status", "char_start", "char_end", "path_token"):
+            getattr(out, f).fill_(-7)
+        plan.run(E, out=out)
+        torch.cuda.synchronize()
+        got = [getattr(out, f).cpu() for f in ("status", "n_frames", "char_start", "char_end", "char_score", "char_start_s",
+                                               "char_end_s", "char_score_r")]
+        got += [out.path_token.cpu()[valid], out.path_logp.cpu()[valid]]
+        for a, c in zip(first, got):
+            assert torch.equal(a.view(torch.uint8), c.view(torch.uint8)), it
+        if it == 5:
+            engine.align_batch(bE, bspec)               # needs far more choice-bit scratch than `plan`
     plan.close()
 
 

@@ -439,6 +439,7 @@ struct wxb_ctx {
     DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, trace;
     int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
     bool want_trace = false;                  // WXB_TRACE=1
+    bool use_graphs = true;                   // WXB_GRAPHS=0 disables graph replay in wxb_plan_run
     size_t chunk_bytes = 64u << 20;           // WXB_CHUNK_MB: emission bytes per pipelined H2D chunk
     std::vector<Arena *> arena_pool;          // metadata arenas of destroyed plans, ready for reuse
     // wxb_align_host staging
@@ -463,6 +464,13 @@ struct wxb_plan {
     Arena *arena = nullptr;
     cudaStream_t last_stream = nullptr;
     bool ran = false;
+    // wxb_plan_run replays a CUDA graph from the third identical call on (same emissions pointer, same outputs)
+    const float *graph_emis = nullptr;
+    wxb_outputs graph_out{};
+    int graph_same = 0;                       // consecutive calls with this key
+    cudaGraphExec_t graph_exec = nullptr;
+    void *graph_scratch[6] = {};              // context scratch pointers baked into the graph (another plan may regrow them)
+    bool graph_off = false;                   // capture failed once: stay eager
     // device views into the arena
     SegDesc *d_segs = nullptr; FinBlock *d_fin = nullptr; int *d_tok4 = nullptr; ShortSeg *d_short = nullptr;
     double *d_t1 = nullptr, *d_ratio = nullptr; unsigned char *d_round_np = nullptr;
@@ -582,6 +590,7 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     c->device = device;
     if (const char *e = getenv("WXB_SIDE_STREAMS")) c->side_streams = std::max(1, std::min(NSIDE, atoi(e)));
     if (const char *e = getenv("WXB_TRACE")) c->want_trace = atoi(e) != 0;
+    if (const char *e = getenv("WXB_GRAPHS")) c->use_graphs = atoi(e) != 0;
     if (const char *e = getenv("WXB_K_TARGET")) g_k_target = std::max(1, std::min(KMAX, atoi(e)));
     if (const char *e = getenv("WXB_TILE_FRAMES")) g_tile_pref = std::max(4, std::min(32, atoi(e)));
     if (const char *e = getenv("WXB_RING_EXTRA")) g_ring_extra = std::max(1, std::min(4, atoi(e)));
@@ -647,6 +656,7 @@ static size_t up256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 static void plan_free(wxb_plan *pl) {
     if (!pl) return;
+    if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->arena) pl->ctx->arena_pool.push_back(pl->arena);
     delete pl;
 }
@@ -985,7 +995,12 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
 
     pl->last_stream = st;
     pl->ran = true;
-    CUDA_TRY(cudaStreamWaitEvent(st, pl->arena->uploaded, 0));     // the plan's metadata upload (ctx stream)
+    {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+        // the plan's metadata upload (ctx stream); while capturing, the caller has already waited for it on the host
+        if (cap == cudaStreamCaptureStatusNone) CUDA_TRY(cudaStreamWaitEvent(st, pl->arena->uploaded, 0));
+    }
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t0, st));
     const int nb = static_cast<int>(pl->buckets.size());
     // every class's backtrack_kernel and finalize_kernel follow its align_kernel on the same stream, so
@@ -1085,8 +1100,56 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     return WXB_OK;
 }
 
+// A plan that is run again and again on the same buffers (steady-state serving, bench.py) is a fixed
+// DAG of ~25 launches over 8 side streams joined by events: from the third identical call on it is
+// replayed as one CUDA graph, which removes the per-step event/launch latencies between steps.
 extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *o, void *stream_, float *elapsed_dp_ms) {
-    return run_impl(pl, emis, nullptr, o, static_cast<cudaStream_t>(stream_), elapsed_dp_ms);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
+    wxb_ctx *c = pl->ctx;
+    if (elapsed_dp_ms || !c->use_graphs || c->want_trace || pl->graph_off || pl->S == 0)
+        return run_impl(pl, emis, nullptr, o, st, elapsed_dp_ms);
+    const bool same = pl->graph_emis == emis && memcmp(&pl->graph_out, o, sizeof(wxb_outputs)) == 0;
+    if (!same) {
+        if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
+        pl->graph_emis = emis;
+        pl->graph_out = *o;
+        pl->graph_same = 0;
+    }
+    ++pl->graph_same;
+    if (pl->graph_same < 3) return run_impl(pl, emis, nullptr, o, st, nullptr);      // eager: allocates scratch, configures kernels
+    CUDA_TRY(cudaSetDevice(c->device));
+    void *scratch[6] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p};
+    if (pl->graph_exec && memcmp(scratch, pl->graph_scratch, sizeof scratch) != 0) {
+        cudaGraphExecDestroy(pl->graph_exec);     // a larger plan regrew the shared scratch since the capture
+        pl->graph_exec = nullptr;
+        return run_impl(pl, emis, nullptr, o, st, nullptr);     // re-establishes the scratch; captured again next call
+    }
+    if (!pl->graph_exec) {
+        CUDA_TRY(cudaEventSynchronize(pl->arena->uploaded));
+        CUDA_TRY(cudaStreamSynchronize(c->main));
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(c->main, cudaStreamCaptureModeThreadLocal);
+        int rc = WXB_OK;
+        if (e == cudaSuccess) {
+            rc = run_impl(pl, emis, nullptr, o, c->main, nullptr);
+            e = cudaStreamEndCapture(c->main, &graph);
+        }
+        if (e == cudaSuccess && rc == WXB_OK) e = cudaGraphInstantiate(&pl->graph_exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess || rc != WXB_OK) {
+            cudaGetLastError();               // clear the sticky capture error; this plan stays eager
+            pl->graph_exec = nullptr;
+            pl->graph_off = true;
+            return run_impl(pl, emis, nullptr, o, st, nullptr);
+        }
+        void *now[6] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p};
+        memcpy(pl->graph_scratch, now, sizeof now);
+    }
+    pl->last_stream = st;
+    pl->ran = true;
+    CUDA_TRY(cudaGraphLaunch(pl->graph_exec, st));
+    return WXB_OK;
 }
 
 extern "C" int wxb_align_device(wxb_ctx *ctx, const wxb_batch *batch, const float *emissions_dev,
