@@ -989,8 +989,10 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     P.path_tok = o->path_token; P.path_logp = o->path_logp;
     P.final_col = o->final_col; P.trellis = o->trellis; P.logprobs = o->logprobs;
     if (c->want_trace) {
-        CUDA_TRY(c->trace.ensure(static_cast<size_t>(std::max(pl->n_desc, 1)) * 32));
+        CUDA_TRY(c->trace.ensure(static_cast<size_t>(std::max(pl->n_desc, 1)) * 32 + 64));
         P.trace = c->trace.as<unsigned long long>();
+        P.trace_hist = P.trace + 4ll * std::max(pl->n_desc, 1);
+        CUDA_TRY(cudaMemsetAsync(P.trace_hist, 0, 64, st));
     }
 
     pl->last_stream = st;
@@ -1280,6 +1282,13 @@ extern "C" int wxb_plan_debug_trace(wxb_plan *pl, uint64_t *rows, int64_t cap_ro
     const int n = static_cast<int>(std::min<int64_t>(pl->n_desc, cap_rows));
     std::vector<unsigned long long> raw(static_cast<size_t>(std::max(n, 1)) * 4);
     CUDA_TRY(cudaMemcpy(raw.data(), c->trace.p, static_cast<size_t>(n) * 32, cudaMemcpyDeviceToHost));
+    {
+        unsigned long long hist[8];
+        CUDA_TRY(cudaMemcpy(hist, c->trace.as<unsigned long long>() + 4ll * std::max(pl->n_desc, 1), 64, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[wxb] frames per scheduler (compute warps | producer warps):");
+        for (int i = 0; i < 4; ++i) fprintf(stderr, "  s%d %llu | %llu", i, hist[2 * i], hist[2 * i + 1]);
+        fprintf(stderr, "\n");
+    }
     for (int i = 0; i < n; ++i) {
         const SegDesc &d = pl->host_descs[i];
         uint64_t *r = rows + 8ll * i;

@@ -63,6 +63,7 @@ struct Params {
     int *path_tok;
     float *path_logp, *final_col, *trellis, *logprobs;
     unsigned long long *trace;   // debug: [4 * n_desc] {t_begin, t_forward_done, t_end, smid} per CTA, or null
+    unsigned long long *trace_hist;   // debug: [4][2] frames handled per scheduler by compute / producer warps, or null
 };
 
 #ifndef WXB_UNROLL
@@ -184,6 +185,11 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         p.trace[4ll * (seg_first + blockIdx.x) + 0] = global_ns();
         p.trace[4ll * (seg_first + blockIdx.x) + 3] = smid;
+    }
+    if (p.trace_hist && lane == 0) {       // debug: frames of work per (scheduler = hardware warp slot % 4, role)
+        uint32_t hw;
+        asm volatile("mov.u32 %0, %warpid;" : "=r"(hw));
+        atomicAdd(p.trace_hist + (hw & 3u) * 2u + (wi == W ? 1u : 0u), static_cast<unsigned long long>(T));
     }
     const SmemLayout L = smem_layout(W, NB, TE, V, EB);
     const uint32_t sm_base = smem_u32(sm);
