@@ -21,7 +21,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: the reference adds and compares float32 values; no contraction anywhere.
 FLAGS = ARCH + ["-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE]
-if os.environ.get("WXB_EXTRA_NVCC_FLAGS"):            # experiments only (e.g. -DWXB_UNROLL=2)
+if os.environ.get("WXB_EXTRA_NVCC_FLAGS"):            # experiments only (e.g. -DWXB_REGS(K)=64)
     FLAGS += os.environ["WXB_EXTRA_NVCC_FLAGS"].split()
 if os.environ.get("WXB_LIB_OUT"):
     LIB = os.environ["WXB_LIB_OUT"]

@@ -535,21 +535,21 @@ static int g_ring_extra = 2;     // WXB_RING_EXTRA (experiments): ring depth = W
 // with many warps); the ring is W+2 deep — every warp on its own tile plus one being filled — or
 // shallower if shared memory says so (any depth >= 2 is deadlock-free).  cp.async.bulk needs
 // 16-byte multiples, i.e. TE % 4 == 0.
-static int pick_shape(int W, int V, int entry, int *TE, int *NB, size_t *smem) {
+static int pick_shape(int W, int V, bool wild, int *TE, int *NB, size_t *smem) {
     const int pref[4] = {32, 16, 8, 4};
     const int want_ctas = std::max(1, (16 + W) / (W + 1));
     int chosen = -1;
     for (int i = 0; i < 4 && chosen < 0; ++i) {
         if (pref[i] > g_tile_pref) continue;
-        if (smem_layout(W, W + g_ring_extra, pref[i], V, entry).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+        if (smem_layout(W, W + g_ring_extra, pref[i], V, wild).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     }
     for (int i = 0; i < 4 && chosen < 0; ++i)         // nothing reaches the occupancy target: the longest tile that fits at all
-        if (pref[i] <= g_tile_pref && smem_layout(W, 2, pref[i], V, entry).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+        if (pref[i] <= g_tile_pref && smem_layout(W, 2, pref[i], V, wild).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     if (chosen < 0) return -1;
     int nb = std::max(2, W + g_ring_extra);
-    while (nb > 2 && smem_layout(W, nb, chosen, V, entry).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
+    while (nb > 2 && smem_layout(W, nb, chosen, V, wild).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
     *TE = chosen; *NB = nb;
-    *smem = smem_layout(W, nb, chosen, V, entry).total;
+    *smem = smem_layout(W, nb, chosen, V, wild).total;
     return 0;
 }
 
@@ -689,7 +689,6 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     pl->W = bt->n_words;
     pl->has_words = bt->n_words > 0;
     pl->has_wild = (bt->flags & WXB_F_WILDCARD) != 0;
-    const int entry = pl->has_wild ? 16 : 8;            // bytes per boundary entry in shared memory (see align_kernel)
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (S == 0) { guard.p = nullptr; *out = pl; return WXB_OK; }
 
@@ -762,7 +761,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     pl->n_short = static_cast<int>(shorts.size());
     {
         int te, nbq; size_t sm;
-        if (pick_shape(wmax, pl->V, entry, &te, &nbq, &sm) != 0)
+        if (pick_shape(wmax, pl->V, pl->has_wild, &te, &nbq, &sm) != 0)
             return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory for a %d-warp segment", pl->V, SMEM_LIMIT, wmax);
     }
     // one launch per (chunk, warps, tokens-per-lane) class; longest-first inside a class: the block
@@ -780,7 +779,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].W * descs[i].K * 32;
         if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W || descs[i].pad != descs[i - 1].pad) {
             Bucket b{descs[i].K, descs[i].W, 0, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad, fin_next, 0};
-            pick_shape(b.W, pl->V, entry, &b.TE, &b.NB, &b.smem);
+            pick_shape(b.W, pl->V, pl->has_wild, &b.TE, &b.NB, &b.smem);
             pl->buckets.push_back(b);
         }
         pl->buckets.back().count += 1;

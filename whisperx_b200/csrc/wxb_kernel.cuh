@@ -66,22 +66,23 @@ struct Params {
     unsigned long long *trace_hist;   // debug: [4][2] frames handled per scheduler by compute / producer warps, or null
 };
 
-#ifndef WXB_UNROLL
-#define WXB_UNROLL 4      // frames per unrolled block of the recurrence (must divide the tile length)
-#endif
+constexpr int UNR = 4;           // frames per unrolled block of the recurrence: boundary values move as float4
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int KMAX = 8;          // largest tokens-per-lane class that is instantiated
 constexpr int WMAX = 31;         // compute warps per CTA (+1 producer warp = 1024 threads)
 
 // Shared-memory carve-up of one CTA (all offsets in bytes from the dynamic smem base).
 struct SmemLayout {
-    uint32_t tile_bytes, off_left, off_xd, off_fin, off_bar, total;
+    uint32_t tile_bytes, off_left, off_eb, off_wild, off_xd, off_fin, off_bar, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int W, int NB, int TE, int V, int entry_bytes = 8) {
+__host__ __device__ inline SmemLayout smem_layout(int W, int NB, int TE, int V, bool wild = false) {
     SmemLayout L;
+    const uint32_t per_ring = static_cast<uint32_t>(NB) * TE * 4u;        // one float per frame of every ring slot
     L.tile_bytes = static_cast<uint32_t>(TE) * V * 4u;                    // TE % 4 == 0 -> multiple of 16
-    L.off_left = static_cast<uint32_t>(NB) * L.tile_bytes;                // left[W+1][NB][TE] {boundary, blank} (+ {wildcard, -})
-    L.off_xd = (L.off_left + static_cast<uint32_t>(W + 1) * NB * TE * static_cast<uint32_t>(entry_bytes) + 15u) & ~15u;   // 32 doubles
+    L.off_left = static_cast<uint32_t>(NB) * L.tile_bytes;                // left[W+1][NB][TE]: column left of each warp's first
+    L.off_eb = L.off_left + static_cast<uint32_t>(W + 1) * per_ring;      // eb[NB][TE]: logp[t, blank]
+    L.off_wild = L.off_eb + per_ring;                                     // wild[NB][TE]: wildcard emission (WILD kernels)
+    L.off_xd = (L.off_wild + (wild ? per_ring : 0u) + 15u) & ~15u;        // 32 doubles
     L.off_fin = L.off_xd + 256u;                                          // trellis[T, N] (one float)
     L.off_bar = L.off_fin + 16u;                                          // tma[NB] full[NB] empty[NB] edge[W][NB]
     L.total = L.off_bar + static_cast<uint32_t>(3 + W) * NB * 8u;
@@ -101,13 +102,8 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_f32x2(uint32_t addr, float a, float b) {
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void sts_f32(uint32_t addr, float a) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
 }
 __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
     float4 v;
@@ -168,10 +164,9 @@ __device__ __forceinline__ void owner_of(int k, int r, int &g, int &slot) {
 
 // WILD: the batch contains wildcard tokens (id -1, an extension over the reference — see DESIGN.md):
 // their emission at frame t is max over non-blank v of logp[t, v]; the producer computes it per frame
-// and it travels with the boundary entries ({boundary, blank, wildcard, -} instead of {boundary, blank}).
+// into its own per-tile array next to the blank log-probs.
 template <int K, bool DEBUG, bool WILD>
 __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(const Params p, const int seg_first, const int NB, const int TE) {
-    constexpr uint32_t EB = WILD ? 16u : 8u;        // bytes per boundary entry
     extern __shared__ __align__(128) unsigned char sm[];
     const int lane = threadIdx.x & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform (uniform registers for the
@@ -191,13 +186,13 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
         asm volatile("mov.u32 %0, %warpid;" : "=r"(hw));
         atomicAdd(p.trace_hist + (hw & 3u) * 2u + (wi == W ? 1u : 0u), static_cast<unsigned long long>(T));
     }
-    const SmemLayout L = smem_layout(W, NB, TE, V, EB);
+    const SmemLayout L = smem_layout(W, NB, TE, V, WILD);
     const uint32_t sm_base = smem_u32(sm);
     const uint32_t bar_tma = sm_base + L.off_bar;
     const uint32_t bar_full = bar_tma + 8u * NB;
     const uint32_t bar_empty = bar_full + 8u * NB;
     const uint32_t bar_edge = bar_empty + 8u * NB;     // [w][b], w = 0..W-1 (row 0 unused)
-    const uint32_t left_stride_w = static_cast<uint32_t>(NB) * TE * EB;   // bytes between left[w] and left[w+1]
+    const uint32_t left_stride_w = static_cast<uint32_t>(NB) * TE * 4u;   // bytes between left[w] and left[w+1]
     const int ntiles = (T + TE - 1) / TE;
     const float *Eg = p.emis + d.emis_off;
 
@@ -238,8 +233,8 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
         uint32_t sph = 0;
         auto scan_next = [&]() {
             mbar_wait(bar_empty + 8u * sb, sph);
-            const unsigned char *fin = sm + L.off_left + static_cast<uint32_t>((W * NB + sb) * TE) * EB;
-            float v = (st0 + lane < T && lane < TE) ? *reinterpret_cast<const float *>(fin + lane * EB) : -INFINITY;
+            const float *fin = reinterpret_cast<const float *>(sm + L.off_left) + (W * NB + sb) * TE;
+            float v = (st0 + lane < T && lane < TE) ? fin[lane] : -INFINITY;
             int vi = st0 + lane;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -314,7 +309,8 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                 }
             }
             // ---- column 0 of the trellis for rows t0 .. t0+n-1 (exclusive float64 prefix) ----
-            unsigned char *col0 = sm + L.off_left + static_cast<uint32_t>(b * TE) * EB;   // left[0][b][:] = {trellis[t, 0], logp[t, blank](, wildcard)}
+            float *col0 = reinterpret_cast<float *>(sm + L.off_left) + b * TE;     // left[0][b][:] = trellis[t, 0]
+            float *ebs = reinterpret_cast<float *>(sm + L.off_eb) + b * TE;        // logp[t, blank]
             const float e0 = (lane < n) ? tb[lane * V] : 0.0f;
             if (lane < n) p.p0[d.frame_base + t0 + lane] = expf(e0);
             float mine_f = INFINITY;
@@ -331,14 +327,14 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             }
             if (lane < n) {
                 const float ebl = tb[lane * V + p.blank];
+                col0[lane] = mine_f;
+                ebs[lane] = ebl;
                 if (WILD) {
                     float wv = -INFINITY;           // max over the non-blank vocabulary
                     for (int v = 0; v < V; ++v)
                         if (v != p.blank) wv = fmaxf(wv, tb[lane * V + v]);
                     p.wild[d.frame_base + t0 + lane] = wv;
-                    *reinterpret_cast<float4 *>(col0 + lane * EB) = make_float4(mine_f, ebl, wv, 0.0f);
-                } else {
-                    *reinterpret_cast<float2 *>(col0 + lane * EB) = make_float2(mine_f, ebl);
+                    (reinterpret_cast<float *>(sm + L.off_wild) + b * TE)[lane] = wv;
                 }
             }
             if (DEBUG) {
@@ -403,7 +399,7 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             ph ^= wrap ? 1u : 0u;
             const int n = min(TE, T - tau * TE);
             mbar_wait(wait_bar0 + 8u * b, ph);
-            if (lane < n) sts_f32x2(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * EB, -INFINITY, 0.0f);
+            if (lane < n) sts_f32(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * 4u, -INFINITY);
             t += n;
             if ((t & 31) == 0) {            // a 32-frame choice word is complete: all zeros
 #pragma unroll
@@ -424,29 +420,24 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             mbar_wait(wait_bar0 + 8u * b, ph);
 
             uint32_t rowaddr = sm_base + b * L.tile_bytes;
-            uint32_t left_in = left_in0 + static_cast<uint32_t>(b * TE) * EB;     // + EB*tt as the tile advances
+            uint32_t left_in = left_in0 + static_cast<uint32_t>(b * TE) * 4u;     // advances with the tile
             uint32_t left_out = left_in + left_stride_w;
-            asm volatile("" : "+r"(left_in), "+r"(left_out));   // materialise once per tile, not per frame under a predicate
+            uint32_t eb_in = sm_base + L.off_eb + static_cast<uint32_t>(b * TE) * 4u;
+            uint32_t wild_in = sm_base + L.off_wild + static_cast<uint32_t>(b * TE) * 4u;
+            asm volatile("" : "+r"(left_in), "+r"(left_out), "+r"(eb_in));   // materialise once per tile, not per frame under a predicate
 
-            // ---- the recurrence (:372-378) ----
-            auto step = [&](int u) {         // u = frame inside the current unrolled block (a literal after unrolling)
-                float4 lv;                                             // {trellis[t, my first column - 1], logp[t, blank](, wildcard)}
-                if (WILD) lv = lds_f32x4(left_in + EB * u);
-                else { const float2 l2 = lds_f32x2(left_in + EB * u); lv = make_float4(l2.x, l2.y, 0.0f, 0.0f); }
-                const float eb = lv.y;
+            // ---- the recurrence (:372-378): one frame ----
+            // eb = logp[t, blank]; lv = trellis[t, first column of this warp - 1] (used by lane 0); wv = wildcard emission
+            auto step = [&](float eb, float lv, float wv) {
                 float left = __shfl_up_sync(FULL, src, 1);
-                if (lane == 0) left = lv.x;
-                if (lane == laneN) {                                   // row t of my last column -> warp wi+1
-                    if (WILD) sts_f32x4(left_out + EB * u, src, eb, lv.z, 0.0f);
-                    else sts_f32x2(left_out + EB * u, src, eb);
-                }
+                if (lane == 0) left = lv;
                 // chg first (it reads the *old* left neighbours), then stay / sign-difference as packed
                 // f32x2 adds (FADD2 on sm_100: one issue slot for two cells; IEEE round-to-nearest per lane)
                 float chg[K];
 #pragma unroll
                 for (int i = K - 1; i >= 0; --i) {
                     float e = lds_f32(rowaddr + tokoff[i]);
-                    if (WILD && ((wmask >> i) & 1u)) e = lv.z;
+                    if (WILD && ((wmask >> i) & 1u)) e = wv;
                     chg[i] = ((i == 0) ? left : R[i - 1]) + e;    // trellis[t, j-1] + emission[t, tokens[j-1]]
                 }
 #pragma unroll
@@ -484,18 +475,29 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                 }
             };
 
+            // four frames at a time: their blank log-probs and left-boundary values arrive as one float4 each,
+            // and the four rows of this warp's last column leave as one float4 (LSU instructions, not issue
+            // slots, are the scarcest resource of this loop: profiles/r1_occupancy_and_pipes.md)
             int tt = 0;
-            for (; tt + WXB_UNROLL <= n; tt += WXB_UNROLL) {
-#pragma unroll
-                for (int u = 0; u < WXB_UNROLL; ++u) step(u);
-                left_in += EB * WXB_UNROLL;
-                left_out += EB * WXB_UNROLL;
+            for (; tt + UNR <= n; tt += UNR) {
+                const float4 e4 = lds_f32x4(eb_in);
+                const float4 l4 = lds_f32x4(left_in);
+                float4 w4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (WILD) w4 = lds_f32x4(wild_in);
+                const float s0 = src; step(e4.x, l4.x, w4.x);
+                const float s1 = src; step(e4.y, l4.y, w4.y);
+                const float s2 = src; step(e4.z, l4.z, w4.z);
+                const float s3 = src; step(e4.w, l4.w, w4.w);
+                if (lane == laneN) sts_f32x4(left_out, s0, s1, s2, s3);    // rows t..t+3 of my last column -> warp wi+1
+                eb_in += 16u; left_in += 16u; left_out += 16u; wild_in += 16u;
                 flush_if_word_done();
             }
-            for (; tt < n; ++tt) {
-                step(0);
-                left_in += EB;
-                left_out += EB;
+            for (; tt < n; ++tt) {             // the last, partial block of a segment
+                const float eb = lds_f32(eb_in), lv = lds_f32(left_in);
+                const float wv = WILD ? lds_f32(wild_in) : 0.0f;
+                if (lane == laneN) sts_f32(left_out, src);
+                step(eb, lv, wv);
+                eb_in += 4u; left_in += 4u; left_out += 4u; wild_in += 4u;
                 flush_if_word_done();
             }
             __syncwarp();
