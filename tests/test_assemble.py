@@ -5,6 +5,7 @@ The per-character values come from the oracle here (torch port: bit-identical to
 the exact rounding / numpy-order mean from the library's host helpers; the GPU tests
 (test_align_gpu.py) run the same scenarios through the kernels."""
 import copy
+import json
 import ctypes as C
 import math
 
@@ -116,3 +117,63 @@ def test_fallback_splitter():
     assert assemble.sentence_spans("Dr. Smith is here. Yes") == [(0, 18), (19, 22)]
     assert assemble.sentence_spans(" lead and trail ") == [(1, 15)]
     assert assemble.blank_id_of({"a": 1, "<pad>": 7, "b": 2}) == 7 and assemble.blank_id_of({"a": 3}) == 0
+
+
+def _device_like_words(lay, cs, ce, sc, lib):
+    ws, we, wsc = [], [], []
+    for g in range(lay.n_groups):
+        idx = lay.group_idx[lay.group_off[g]:lay.group_off[g + 1]]
+        al = [i for i in idx if i >= 0]
+        if not al:
+            ws.append(math.nan); we.append(math.nan); wsc.append(math.nan)
+            continue
+        z = np.array([sc[i] if i >= 0 else 0.0 for i in idx], np.float64)
+        ws.append(cs[al[0]]); we.append(ce[al[-1]])
+        wsc.append(lib.wxb_round3_np(lib.wxb_pairwise_sum(z.ctypes.data_as(C.POINTER(C.c_double)), len(z)) / len(al)))
+    return ws, we, wsc
+
+
+@pytest.mark.parametrize("lang", ["en", "ja"])
+def test_random_texts_match_the_pandas_tables(lang):
+    """Differential test of the record assembly (alignment.py:252-347) on random texts: odd spacing,
+    unknown characters, words straddling sentence windows, sentences without any aligned character,
+    both interpolation methods, with and without char alignments — against the oracle's pandas
+    restatement fed the same per-character frames and scores."""
+    lib = _native.load()
+    rng = np.random.default_rng(17 if lang == "en" else 18)
+    alphabet = list("abcdefg hij  klm.!?,'0123 ") + ["é", "-"]
+    for case in range(120):
+        L = int(rng.integers(1, 60))
+        text = "".join(rng.choice(alphabet, L))
+        if not text.strip():
+            text = text + "a"
+        seg = {"start": round(float(rng.uniform(0, 50)), 3), "text": text}
+        seg["end"] = round(seg["start"] + float(rng.uniform(0.3, 20)), 3)
+        transcript = [seg]
+        assemble.prepare_transcript(transcript, DICTIONARY, lang)
+        ref_seg = {"start": seg["start"], "end": seg["end"], "text": text}
+        ref_port.prepare_segments([ref_seg], DICTIONARY, lang, regex_spans)
+        assert ref_seg["clean_char"] == seg["clean_char"] and ref_seg["clean_cdx"] == seg["clean_cdx"], text
+        assert ref_seg["clean_wdx"] == seg["clean_wdx"] and [tuple(x) for x in ref_seg["sentence_spans"]] == seg["sentence_spans"]
+        N = len(seg["clean_char"])
+        if N == 0:
+            continue
+        T = N + int(rng.integers(0, 80))
+        starts = np.sort(rng.choice(T, N, replace=False))
+        ends = np.append(starts[1:], min(T, starts[-1] + int(rng.integers(1, 5))))
+        scores = np.round(rng.random(N) ** 2, 6)
+        chars = [ref_port.Segment(c, int(a), int(b), float(s)) for c, a, b, s in zip(seg["clean_char"], starts, ends, scores)]
+        ratio = (seg["end"] - seg["start"]) / T
+        method = "nearest" if case % 2 else "linear"
+        want_chars = bool(case % 3 == 0)
+        exp = ref_port.segment_tables(ref_seg, chars, ratio, lang, method, want_chars)
+        cs = [lib.wxb_round3(c.start * ratio + seg["start"]) for c in chars]
+        ce = [lib.wxb_round3(c.end * ratio + seg["start"]) for c in chars]
+        sc = [lib.wxb_round3(c.score) for c in chars]
+        lay = assemble.layout_segment(text, seg["clean_cdx"], seg["sentence_spans"], lang)
+        ws, we, wsc = _device_like_words(lay, cs, ce, sc, lib)
+        got = assemble.assemble_segment(text, seg["clean_cdx"], lay, seg["sentence_spans"], lang, cs, ce, sc, ws, we, wsc,
+                                        method, want_chars)
+        exp = json.loads(json.dumps(exp, default=float))
+        d = same_records(got, exp)
+        assert d is None, (text, method, want_chars, d)
