@@ -225,6 +225,9 @@ def run_ours(args):
 
     import torch
     import torch.distributed as dist
+    # one process per GPU: run on (and allocate the pinned staging buffers from) the GPU's own socket
+    from whisperx_b200 import numa
+    bound = numa.bind_process_to_gpu(local) if not args.no_numa_bind else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -307,7 +310,8 @@ def run_ours(args):
                        "segments_per_gpu": nseg, "workload_id": args.workload, "audio_hours_per_gpu": batch.audio_seconds / 3600.0,
                        "cells_per_gpu": int(plan.cells), "emission_bytes_per_gpu": int(host_em.numel() * 4),
                        "l2": f"inputs ({host_em.numel() * 4 / 1e6:.0f} MB per step) larger than L2 (126 MB); no explicit flush",
-                       "failed_segments": failed},
+                       "failed_segments": failed,
+                       "host_cpus_bound_to_gpu_socket": (len(bound) if bound else None)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
                          "kernel": "wxb::align_kernel<K,false> (+ its finalize_kernel): one launch per (warps, tokens-per-lane) class, "
@@ -340,6 +344,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's local CPU cores")
     ap.add_argument("--workload", default=WORKLOAD, choices=["c2", "c5", "c4"],
                     help="c2 = the benchmark line; c5 (all 30 s segments, one K class) / c4 are profiling workloads")
     ap.add_argument("--segments", type=int, default=SEGMENTS_PER_GPU)
