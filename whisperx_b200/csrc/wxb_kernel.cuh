@@ -4,7 +4,7 @@
 // Replaces, for a whole batch of segments, the reference's per-segment Python:
 //   log_softmax            whisperx/alignment.py:233      (producer warp, fused into the tile staging)
 //   get_trellis            whisperx/alignment.py:359-379  (compute warps: recurrence, token axis in registers)
-//   backtrack              whisperx/alignment.py:387-421  (backtrack_kernel in wxb_align.cu: walk over packed choice bits)
+//   backtrack              whisperx/alignment.py:387-421  (backtrack_kernel in wxb_small.cuh: walk over packed choice bits)
 //   merge_repeats          whisperx/alignment.py:438-454  (finalize_kernel: per-token start/end/mean prob)
 //   char timestamps        whisperx/alignment.py:252-264  (finalize_kernel: exact decimal rounding)
 //
