@@ -148,6 +148,10 @@ int  wxb_align_device(wxb_ctx *ctx, const wxb_batch *batch, const float *emissio
 int  wxb_align_host(wxb_ctx *ctx, const wxb_batch *batch, const float *emissions_host,
                     const wxb_outputs *out_host);
 
+/* Emission bytes per host->device chunk of wxb_align_host (default 64 MiB, env WXB_CHUNK_MB).  Any value >= 1
+ * is legal — a chunk may be smaller than one segment.  Returns the previous value. */
+int64_t wxb_set_chunk_bytes(wxb_ctx *ctx, int64_t bytes);
+
 /* ---- kernel (i) on its own: log_softmax(dim=-1) over [rows, V] (alignment.py:233) ----
  * Same arithmetic, in the same order, as the fused staging inside wxb_plan_run. */
 int  wxb_log_softmax_device(wxb_ctx *ctx, const float *logits_dev, int64_t rows, int32_t vocab,

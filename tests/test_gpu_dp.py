@@ -418,3 +418,38 @@ def test_wildcard_tokens_extension(engine, V, blank):
     from whisperx_b200._native import NativeError
     with pytest.raises(NativeError, match="outside"):
         run(engine, cases[:2], V, blank)
+
+
+@pytest.mark.parametrize("chunk_bytes", [4096, 150_000, 3_000_000])
+def test_host_path_with_tiny_chunks(engine, chunk_bytes):
+    """wxb_align_host streams the emissions in chunks and lets every class wait only for the chunk holding its
+    segments' last rows; chunks smaller than one segment (4 KB = 35 rows) and chunks of a few segments must give
+    the device path's bytes, word reduction and per-chunk result copies included."""
+    b = synth.make_batch(96, "c2", align_frames=4, kind="planted")
+    S = 96
+    rng = np.random.default_rng(5)
+    word_off, wchar_off, wchar_idx = [0], [0], []
+    for s in range(S):
+        N = int(b.tok_off[s + 1] - b.tok_off[s]); k = 0; nw = 0
+        while k < N:
+            L = int(rng.integers(1, 9))
+            wchar_idx += list(range(k, min(k + L, N))); wchar_off.append(len(wchar_idx)); k += L; nw += 1
+        word_off.append(word_off[-1] + nw)
+    spec = BatchSpec(frame_off=b.frame_off, frame_len=b.frame_len, tok_off=b.tok_off, tokens=b.tokens, vocab=b.vocab,
+                     blank_id=b.blank, logits=True, seg_t1=np.arange(S) * 30.0, seg_ratio=b.durations / b.frame_len,
+                     word_off=word_off, wchar_off=wchar_off, wchar_idx=wchar_idx)
+    dev = engine.align_batch(torch.from_numpy(b.emissions).cuda(), spec, want=("path",)).cpu()
+    old = engine._lib.wxb_set_chunk_bytes(engine._ctx, chunk_bytes)
+    try:
+        host = engine.align_batch_host(b.emissions, spec, want=("path",))
+    finally:
+        engine._lib.wxb_set_chunk_bytes(engine._ctx, old)
+    valid = np.zeros(int(b.frame_off[-1]), bool)
+    for s0, T in zip(b.frame_off[:-1], b.frame_len):
+        valid[int(s0):int(s0) + int(T)] = True
+    for f in ("status", "n_frames", "char_start", "char_end", "char_score", "char_start_s", "char_end_s", "char_score_r",
+              "word_start_s", "word_end_s", "word_score"):
+        a, c = getattr(dev, f), getattr(host, f)
+        assert torch.equal(a.view(torch.uint8), c.view(torch.uint8)), f
+    assert torch.equal(dev.path_token[torch.from_numpy(valid)], host.path_token[torch.from_numpy(valid)])
+    assert int(dev.status.sum()) == 0

@@ -306,6 +306,13 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     delete c;
 }
 
+extern "C" int64_t wxb_set_chunk_bytes(wxb_ctx *ctx, int64_t bytes) {
+    if (!ctx) return -1;
+    const int64_t old = static_cast<int64_t>(ctx->chunk_bytes);
+    if (bytes >= 1) ctx->chunk_bytes = static_cast<size_t>(bytes);
+    return old;
+}
+
 extern "C" int wxb_get_limits(const wxb_ctx *ctx, wxb_limits *out) {
     if (!ctx || !out) return fail(WXB_EINVAL, "wxb_get_limits: NULL argument");
     int vmax = 1;
