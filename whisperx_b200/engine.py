@@ -7,6 +7,7 @@ hand-written sm_100a kernels of libwxb_align.so.  No CPU fallback exists.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -174,7 +175,8 @@ class Plan:
         self.spec = spec           # keeps the host arrays alive
         self._h = C.c_void_p()
         cb = spec.to_c()
-        N.check(engine._lib.wxb_plan_create(engine._ctx, C.byref(cb), C.byref(self._h)), "wxb_plan_create")
+        with engine._lock:
+            N.check(engine._lib.wxb_plan_create(engine._ctx, C.byref(cb), C.byref(self._h)), "wxb_plan_create")
         cells, alg, short = C.c_int64(), C.c_int64(), C.c_int64()
         N.check(engine._lib.wxb_plan_stats(self._h, C.byref(cells), C.byref(alg), C.byref(short)), "wxb_plan_stats")
         self.cells, self.alg_bytes, self.n_shortcut = cells.value, alg.value, short.value
@@ -188,7 +190,7 @@ class Plan:
             out = _alloc_outputs(self.spec, eng.device, want)
         co = out.to_c()
         ms = C.c_float(0.0)
-        with torch.cuda.device(eng.device):
+        with eng._lock, torch.cuda.device(eng.device):
             stream = torch.cuda.current_stream(eng.device).cuda_stream
             N.check(eng._lib.wxb_plan_run(self._h, emissions.data_ptr(), C.byref(co), stream,
                                           C.byref(ms) if timed else None), "wxb_plan_run")
@@ -198,7 +200,8 @@ class Plan:
 
     def close(self):
         if self._h:
-            self.engine._lib.wxb_plan_destroy(self._h)
+            with self.engine._lock:
+                self.engine._lib.wxb_plan_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -221,6 +224,8 @@ class AlignEngine:
                                "(there is no CPU fallback).")
         self._lib = N.load()
         self._ctx = C.c_void_p()
+        # a wxb_ctx owns scratch buffers and side streams: one native call at a time per engine
+        self._lock = threading.RLock()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", idx)
         torch.cuda.init()
@@ -257,12 +262,13 @@ class AlignEngine:
 
     def align_batch(self, emissions: torch.Tensor, spec: BatchSpec, want: Sequence[str] = ()) -> BatchResult:
         """get_trellis + backtrack + merge_repeats (+ timestamps / words) for every segment."""
-        plan = Plan(self, spec)
-        try:
-            out = plan.run(emissions, want=want)
-            torch.cuda.current_stream(self.device).synchronize()
-        finally:
-            plan.close()
+        with self._lock:
+            plan = Plan(self, spec)
+            try:
+                out = plan.run(emissions, want=want)
+                torch.cuda.current_stream(self.device).synchronize()
+            finally:
+                plan.close()
         return out
 
     def align_batch_host(self, emissions_host, spec: BatchSpec, want: Sequence[str] = (),
@@ -278,7 +284,8 @@ class AlignEngine:
         if out is None:
             out = _alloc_outputs(spec, "cpu", want, pin=True)
         cb, co = spec.to_c(), out.to_c()
-        N.check(self._lib.wxb_align_host(self._ctx, C.byref(cb), eptr, C.byref(co)), "wxb_align_host")
+        with self._lock:
+            N.check(self._lib.wxb_align_host(self._ctx, C.byref(cb), eptr, C.byref(co)), "wxb_align_host")
         return out
 
     def log_softmax(self, logits: torch.Tensor) -> torch.Tensor:
