@@ -453,3 +453,21 @@ def test_host_path_with_tiny_chunks(engine, chunk_bytes):
         assert torch.equal(a.view(torch.uint8), c.view(torch.uint8)), f
     assert torch.equal(dev.path_token[torch.from_numpy(valid)], host.path_token[torch.from_numpy(valid)])
     assert int(dev.status.sum()) == 0
+
+
+def test_maximum_transcript_length(engine):
+    """The largest transcript the build accepts: 31 compute warps x 32 lanes x 8 columns = 7,936 tokens in one CTA
+    of 1,024 threads; one more token is refused with a clear error."""
+    from whisperx_b200._native import NativeError
+    assert engine.limits.max_tokens == 31 * 32 * 8
+    rng = np.random.default_rng(8)
+    N = engine.limits.max_tokens
+    T = N + 64
+    cases = [(logprobs(rng, T, 29), rng.integers(0, 29, N).astype(np.int32)),
+             (logprobs(rng, 300, 29), rng.integers(0, 29, 120).astype(np.int32))]
+    spec, res = run(engine, cases, 29, 0, align=4, want=("path",))
+    check_against_oracle(spec, res, cases, 0, full=False)
+    assert int(res.status[0]) == 0
+    too_long = [(logprobs(rng, N + 70, 29), rng.integers(0, 29, N + 1).astype(np.int32))]
+    with pytest.raises(NativeError, match="at most"):
+        run(engine, too_long, 29, 0, want=())
