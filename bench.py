@@ -314,8 +314,9 @@ def run_ours(args):
                        "host_cpus_bound_to_gpu_socket": (len(bound) if bound else None)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
-                         "kernel": "wxb::align_kernel<K,false> (+ its finalize_kernel): one launch per (warps, tokens-per-lane) class, "
-                                   "run concurrently on side streams and timed together with CUDA events on the launching stream",
+                         "kernel": "wxb::align_kernel<K,false,false> followed by its backtrack_kernel and finalize_kernel: one such chain per "
+                                   "(warps, tokens-per-lane) class, the chains run concurrently on side streams and are timed together "
+                                   "with CUDA events on the launching stream (ncu share of the three: 69 / 23 / 8 %, profiles/)",
                          "kernel_ms": dp, "algorithmic_bytes_per_step": int(plan.alg_bytes),
                          "note": "algorithmic bytes = sum(4*T*V + 20*N) per step; traffic = ncu dram read+write summed over the "
                                  "step's align_kernel launches (profiles/); the recurrence is issue-bound, not HBM-bound (DESIGN.md 4.1)"},
