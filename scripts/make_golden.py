@@ -143,6 +143,31 @@ ALIGN_SCENARIOS = {
     "en_linear": dict(lang="en", audio_s=8.0, interpolate_method="linear", segments=[
         dict(start=0.0, end=6.0, text="One two. 33 44! Five six. 7? eight nine."),
     ]),
+    # sentences without any alignable character at the start, in the middle (two in a row) and at the end:
+    # NaN bounds -> nearest interpolation, ffill / bfill, and groupby-merge of sentences that end up with equal keys
+    "en_nan_sentences": dict(lang="en", audio_s=20.0, return_char_alignments=True, segments=[
+        dict(start=0.0, end=7.0, text="2024! Hello there. 123. 456? General Kenobi! 789."),
+        dict(start=7.0, end=9.0, text="99. 98. 97."),
+        dict(start=9.0, end=15.0, text="Only one sentence here"),
+        dict(start=15.0, end=19.5, text="A. B. 1. C."),
+    ]),
+    "en_nan_linear": dict(lang="en", audio_s=12.0, interpolate_method="linear", segments=[
+        dict(start=0.25, end=11.0, text="7. first words. 8. 9. more words here! 10."),
+    ]),
+    # numpy-typed segment times (np.float64 arithmetic and numpy rounding of the timestamps)
+    "en_numpy_times": dict(lang="en", audio_s=10.0, numpy_times=True, return_char_alignments=True, segments=[
+        dict(start=0.125, end=4.375, text="Rounding follows numpy here. Not python!"),
+        dict(start=4.375, end=9.8125, text="half way cases matter"),
+    ]),
+    "zh_like": dict(lang="zh", audio_s=7.0, segments=[
+        dict(start=0.0, end=3.3, text="ab c。de!f g"),
+        dict(start=3.3, end=6.9, text=" xy z? 12 w "),
+    ]),
+    "en_long": dict(lang="en", audio_s=31.0, segments=[
+        dict(start=0.0, end=30.0, text="The birch canoe slid on the smooth planks. Glue the sheet to the dark blue background. "
+             "It's easy to tell the depth of a well. These days a chicken leg is a rare dish. Rice is often served in round bowls. "
+             "The juice of lemons makes fine punch. The box was thrown beside the parked truck."),
+    ]),
 }
 
 
@@ -178,6 +203,9 @@ def make_align(A):
             logits.append(torch.from_numpy(x))
         model = ScriptedModel(logits)
         transcript = [dict(s) for s in sc["segments"]]
+        if sc.get("numpy_times"):
+            for t in transcript:
+                t["start"], t["end"] = np.float64(t["start"]), np.float64(t["end"])
         emissions = []
         # capture the log-probs the reference actually used
         orig = A.get_trellis
@@ -198,6 +226,7 @@ def make_align(A):
         out_json[name] = dict(lang=sc["lang"], audio_s=sc["audio_s"], audio_samples=int(audio.shape[0]),
                               interpolate_method=sc.get("interpolate_method", "nearest"),
                               return_char_alignments=sc.get("return_char_alignments", False),
+                              numpy_times=sc.get("numpy_times", False),
                               segments=sc["segments"], n_emissions=len(emissions),
                               mutated_inputs=[{k: v for k, v in t.items() if k in ("clean_char", "clean_cdx", "clean_wdx", "sentence_spans")} for t in transcript],
                               result=json.loads(json.dumps(res, default=float)))

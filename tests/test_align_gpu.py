@@ -36,6 +36,9 @@ def test_golden_scenarios(wxa, golden_align, capsys):
     for name, m in meta.items():
         model = ScriptedModel([arr[f"{name}_E{i}"] for i in range(m["n_emissions"])], "cuda:0")
         transcript = copy.deepcopy(m["segments"])
+        if m.get("numpy_times"):
+            for t in transcript:
+                t["start"], t["end"] = np.float64(t["start"]), np.float64(t["end"])
         audio = np.zeros(m["audio_samples"], np.float32)
         res = wxa.align(transcript, model, {"language": m["lang"], "dictionary": DICTIONARY, "type": "torchaudio"},
                         audio, "cuda:0", interpolate_method=m["interpolate_method"],

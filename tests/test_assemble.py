@@ -29,6 +29,7 @@ def _host_align(meta, emissions, lib):
     """align() with the DP done by the oracle and everything else by the product's host code."""
     lang = meta["lang"]
     transcript = copy.deepcopy(meta["segments"])
+    tround = lib.wxb_round3_np if meta.get("numpy_times") else lib.wxb_round3     # np.float64 times round numpy's way
     assemble.prepare_transcript(transcript, DICTIONARY, lang)
     max_dur = meta["audio_samples"] / 16000
     out, k = [], 0
@@ -46,8 +47,8 @@ def _host_align(meta, emissions, lib):
             out.append(plain)
             continue
         ratio = (seg["end"] - seg["start"]) * 1 / E.shape[0]
-        cs = [lib.wxb_round3(c.start * ratio + seg["start"]) for c in chars]
-        ce = [lib.wxb_round3(c.end * ratio + seg["start"]) for c in chars]
+        cs = [tround(c.start * ratio + seg["start"]) for c in chars]
+        ce = [tround(c.end * ratio + seg["start"]) for c in chars]
         sc = [lib.wxb_round3(c.score) for c in chars]
         lay = assemble.layout_segment(seg["text"], seg["clean_cdx"], seg["sentence_spans"], lang)
         ws, we, wsc = [], [], []
