@@ -100,3 +100,31 @@ def test_pandas_mean_is_zero_filled_pairwise():
             s = pd.Series(np.where(mask, np.nan, a))
             z = np.where(mask, 0.0, a)
             assert s.mean() == c_oracle.pairwise_sum(z) / int((~mask).sum())
+
+
+def test_two_restatements_agree_on_random_cases():
+    """The scalar C port and the torch port are independent restatements of the same reference lines
+    (and of the wildcard extension): on random shapes, vocabularies, blank ids, ties and wildcards they
+    must produce the same trellis bits, the same path and the same merged segments."""
+    rng = np.random.default_rng(99)
+    for case in range(60):
+        V = int(rng.choice([2, 5, 29, 40]))
+        blank = int(rng.integers(0, V))
+        T = int(rng.integers(1, 70))
+        N = int(rng.integers(1, T + 3))
+        x = rng.standard_normal((T, V)).astype(np.float32) * 3
+        E = torch.log_softmax(torch.from_numpy(x), -1)
+        if case % 3 == 0:
+            E = torch.round(E * 4) / 4
+        tok = rng.integers(0, V, N).astype(np.int32)
+        if case % 2:
+            tok[rng.random(N) < 0.3] = -1            # wildcard extension
+        Rc = c_oracle.forward_trellis(E.numpy(), tok, blank)
+        Rt = ref_port.forward_trellis(E, tok.tolist(), blank)
+        assert np.array_equal(Rc.view(np.int32), Rt.numpy().view(np.int32)), (case, T, N, V)
+        segs, _ = ref_port.align_tokens(E, tok.tolist(), blank, "x" * N)
+        rc, cs, ce, sc, ts = c_oracle.align_segment(E.numpy(), tok, blank)
+        assert (segs is None) == (rc != 0), (case, T, N)
+        if segs is not None:
+            assert [s.start for s in segs] == cs.tolist() and [s.end for s in segs] == ce.tolist()
+            np.testing.assert_allclose([s.score for s in segs], sc, rtol=1e-6, atol=0)
