@@ -471,3 +471,35 @@ def test_maximum_transcript_length(engine):
     too_long = [(logprobs(rng, N + 70, 29), rng.integers(0, 29, N + 1).astype(np.int32))]
     with pytest.raises(NativeError, match="at most"):
         run(engine, too_long, 29, 0, want=())
+
+
+@pytest.mark.parametrize("V,blank", [(512, 0), (2304, 1), (3503, 3502), (7001, 0)])
+def test_wide_vocabularies_shorten_the_tiles(engine, V, blank):
+    """The reference's default zh / ja models (alignment.py:34-57) have vocabularies in the thousands:
+    the planner then picks 16-, 8- or 4-frame tiles so the ring still fits shared memory.  Same bit-exact
+    bar, log-prob and fused-logit input, one- and many-warp segments, unaligned row offsets."""
+    rng = np.random.default_rng(V)
+    cases = []
+    for T, N in ((1, 1), (7, 3), (50, 20), (90, 90), (130, 70), (200, 199), (160, 161)):
+        cases.append((logprobs(rng, T, V, ties=(T % 2 == 0)), rng.integers(0, V, N).astype(np.int32)))
+    for align in (1, 4):
+        spec, res = run(engine, cases, V, blank, align, no_shortcut=True)
+        check_against_oracle(spec, res, cases, blank)
+    # fused log-softmax on raw logits: paths must be those of the DP over the engine's own log-probs
+    raw = [(rng.standard_normal(E.shape).astype(np.float32) * 4, tk) for E, tk in cases]
+    E, fo, fl, to, tok = concat_cases(raw, V, 1)
+    spec = BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank, logits=True, no_shortcut=True)
+    res = engine.align_batch(torch.from_numpy(E).cuda(), spec, want=("path", "logprobs")).cpu()
+    lp = res.logprobs.view(-1, V).numpy()
+    mine = [(lp[fo[s]:fo[s] + fl[s]].copy(), raw[s][1]) for s in range(len(raw))]
+    for (m, _), (r, _) in zip(mine, raw):
+        np.testing.assert_allclose(m, torch.log_softmax(torch.from_numpy(r), -1).numpy(), rtol=0, atol=2e-5)   # a few ulp at |logp| ~ 20-30 (fp32 sum of V terms)
+    check_against_oracle(BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank), res, mine, blank, full=False)
+
+
+def test_vocabulary_beyond_the_limit_is_refused(engine):
+    from whisperx_b200._native import NativeError
+    V = int(engine.limits.max_vocab) + 1
+    E = torch.zeros((4, V), device="cuda")
+    with pytest.raises(NativeError):
+        engine.align_batch(E, BatchSpec(frame_off=[0, 4], tok_off=[0, 2], tokens=[1, 2], vocab=V))
