@@ -495,6 +495,26 @@ def test_wide_vocabularies_shorten_the_tiles(engine, V, blank):
     for (m, _), (r, _) in zip(mine, raw):
         np.testing.assert_allclose(m, torch.log_softmax(torch.from_numpy(r), -1).numpy(), rtol=0, atol=2e-5)   # a few ulp at |logp| ~ 20-30 (fp32 sum of V terms)
     check_against_oracle(BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank), res, mine, blank, full=False)
+    # the same logits without asking for the log-probs (scratch buffer), replayed (CUDA graph from the 3rd run),
+    # and through the host entry point in small chunks (normalised in place chunk by chunk): same bytes
+    Ed = torch.from_numpy(E).cuda()
+    plan = engine.plan(spec)
+    outs = None
+    for _ in range(4):
+        outs = plan.run(Ed, out=outs, want=("path",))
+    torch.cuda.synchronize()
+    again = outs.cpu()
+    plan.close()
+    old = engine._lib.wxb_set_chunk_bytes(engine._ctx, 40 * V * 4)
+    try:
+        host = engine.align_batch_host(E, spec, want=("path", "logprobs"))
+        host2 = engine.align_batch_host(E, spec, want=("path",))
+    finally:
+        engine._lib.wxb_set_chunk_bytes(engine._ctx, old)
+    for f in ("status", "n_frames", "char_start", "char_end", "char_score", "path_token", "path_logp"):
+        for other in (again, host, host2):
+            assert torch.equal(getattr(res, f).view(torch.uint8), getattr(other, f).view(torch.uint8)), f
+    assert torch.equal(res.logprobs.view(torch.int32), host.logprobs.view(torch.int32))
 
 
 def test_vocabulary_beyond_the_limit_is_refused(engine):

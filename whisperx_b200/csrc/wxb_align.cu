@@ -102,7 +102,8 @@ struct wxb_ctx {
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<cudaEvent_t> ev_chunk;        // one per emission chunk in flight
-    DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, trace;
+    std::vector<cudaEvent_t> ev_soft;         // wide-vocabulary logits: chunk normalised
+    DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, trace, wide_lp;
     int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
     bool want_trace = false;                  // WXB_TRACE=1
     bool use_graphs = true;                   // WXB_GRAPHS=0 disables graph replay in wxb_plan_run
@@ -135,7 +136,7 @@ struct wxb_plan {
     wxb_outputs graph_out{};
     int graph_same = 0;                       // consecutive calls with this key
     cudaGraphExec_t graph_exec = nullptr;
-    void *graph_scratch[6] = {};              // context scratch pointers baked into the graph (another plan may regrow them)
+    void *graph_scratch[7] = {};              // context scratch pointers baked into the graph (another plan may regrow them)
     bool graph_off = false;                   // capture failed once: stay eager
     // device views into the arena
     SegDesc *d_segs = nullptr; FinBlock *d_fin = nullptr; int *d_tok4 = nullptr; ShortSeg *d_short = nullptr;
@@ -284,13 +285,14 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->wild, &c->nframes_scratch, &c->h_emis, &c->h_path_tok};
+    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->wild, &c->nframes_scratch, &c->wide_lp, &c->h_emis, &c->h_path_tok};
     for (DevBuf *b : bufs) b->release();
     for (auto &b : c->h_i32) b.release();
     for (auto &b : c->h_f64) b.release();
     for (auto &b : c->h_f32) b.release();
     for (Arena *a : c->arena_pool) { a->release(); delete a; }
     for (cudaEvent_t ev : c->ev_chunk) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->ev_soft) cudaEventDestroy(ev);
     if (c->main) cudaStreamDestroy(c->main);
     if (c->copy) cudaStreamDestroy(c->copy);
     if (c->d2h) cudaStreamDestroy(c->d2h);
@@ -595,6 +597,22 @@ extern "C" int wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg
     return WXB_OK;
 }
 
+// torch.log_softmax over `rows` rows of V floats (alignment.py:233); in == out is allowed.
+static int launch_log_softmax(const float *in, float *out, int64_t rows, int V, cudaStream_t st) {
+    const size_t row_bytes = static_cast<size_t>(V) * 4;
+    if (row_bytes > static_cast<size_t>(SMEM_LIMIT)) return fail(WXB_EUNSUPPORTED, "log_softmax: vocab %d too large", V);
+    int rpc = static_cast<int>(std::min<size_t>(128, (40 * 1024) / row_bytes));
+    if (rpc >= 4) rpc &= ~3;
+    if (rpc < 4) rpc = 4;                                   // wide rows: one per warp of the CTA
+    while (rpc > 1 && static_cast<size_t>(rpc) * row_bytes > static_cast<size_t>(SMEM_LIMIT)) --rpc;
+    const size_t smem = static_cast<size_t>(rpc) * row_bytes;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(log_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const long long blocks = (rows + rpc - 1) / rpc;
+    log_softmax_kernel<<<static_cast<unsigned>(blocks), 128, smem, st>>>(in, out, rows, V, rpc);
+    CUDA_TRY(cudaGetLastError());
+    return WXB_OK;
+}
+
 // ------------------------------------------------------------------ ABI: run
 // chunk_ready != nullptr: pipelined host path — chunk c of the emissions is on its way to `emis`
 // on the copy stream and chunk_ready[c] fires when it has landed; the kernels of a segment wait
@@ -624,13 +642,28 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     const bool logits = (pl->flags & WXB_F_LOGITS) != 0;
     if (o->logprobs && !logits) return fail(WXB_EINVAL, "wxb_plan_run: logprobs output is only produced with WXB_F_LOGITS");
     const bool debug = o->trellis || o->final_col;
+    // Wide vocabularies: one producer warp per segment cannot normalise thousands of symbols per frame
+    // at the rate the recurrence consumes them (measured 7.1 ms fused vs 0.38 + 0.27 ms split at
+    // V = 2,304), so the rows go through log_softmax_kernel first — into the caller's logprobs buffer if
+    // there is one, in place when the emissions sit in our own staging buffer (host path), else into
+    // scratch — and the recurrence then runs on log-probs.  Same arithmetic, same bits as the fused way.
+    const bool wide_logits = logits && pl->V > wxb::WIDE_V;
 
     wxb_ctx *c = pl->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(c->bits.ensure(static_cast<size_t>(std::max<long long>(pl->bits_words, 1)) * 4));
     CUDA_TRY(c->p0.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
     if (pl->has_wild) CUDA_TRY(c->wild.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
-    if (logits) {
+    float *wide_dst = nullptr;
+    if (wide_logits) {
+        if (o->logprobs) wide_dst = o->logprobs;
+        else if (chunk_ready) wide_dst = const_cast<float *>(emis);       // c->h_emis, ours
+        else {
+            CUDA_TRY(c->wide_lp.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * pl->V * 4));
+            wide_dst = c->wide_lp.as<float>();
+        }
+    }
+    if (logits && !wide_logits) {
         CUDA_TRY(c->rowmax.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
         CUDA_TRY(c->rowlse.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
     }
@@ -650,7 +683,8 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     P.rowmax = c->rowmax.as<float>();
     P.rowlse = c->rowlse.as<float>();
     P.wild = c->wild.as<float>();
-    P.V = pl->V; P.blank = pl->blank; P.is_logits = logits ? 1 : 0;
+    P.V = pl->V; P.blank = pl->blank; P.is_logits = (logits && !wide_logits) ? 1 : 0;
+    if (wide_logits) P.emis = wide_dst;
     P.status = o->status; P.nframes = nframes;
     P.c_start = o->char_start; P.c_end = o->char_end; P.c_score = o->char_score;
     if (want_sec) {
@@ -659,7 +693,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
         P.seg_round_np = pl->has_round_np ? pl->d_round_np : nullptr;
     }
     P.path_tok = o->path_token; P.path_logp = o->path_logp;
-    P.final_col = o->final_col; P.trellis = o->trellis; P.logprobs = o->logprobs;
+    P.final_col = o->final_col; P.trellis = o->trellis; P.logprobs = wide_logits ? nullptr : o->logprobs;
     if (c->want_trace) {
         CUDA_TRY(c->trace.ensure(static_cast<size_t>(std::max(pl->n_desc, 1)) * 32 + 64));
         P.trace = c->trace.as<unsigned long long>();
@@ -677,6 +711,31 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     }
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t0, st));
     const int nb = static_cast<int>(pl->buckets.size());
+    const cudaEvent_t *rows_ready = chunk_ready;        // what a class waits for before it reads its chunk
+    if (wide_logits && pl->sum_T > 0) {
+        if (!chunk_ready) {
+            int rc = launch_log_softmax(emis, wide_dst, pl->sum_T, pl->V, st);
+            if (rc != WXB_OK) return rc;
+        } else {
+            // host path: normalise each chunk on the main stream as it lands; the classes wait for that
+            const int n_chunks = static_cast<int>(pl->chunk_seg.size()) - 1;
+            while (static_cast<int>(c->ev_soft.size()) < n_chunks) {
+                cudaEvent_t ev;
+                CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                c->ev_soft.push_back(ev);
+            }
+            for (int k = 0; k < n_chunks; ++k) {
+                const int64_t r0 = pl->chunk_row[k], r1 = pl->chunk_row[k + 1];
+                CUDA_TRY(cudaStreamWaitEvent(st, chunk_ready[k], 0));
+                if (r1 > r0) {
+                    int rc = launch_log_softmax(emis + r0 * pl->V, wide_dst + r0 * pl->V, r1 - r0, pl->V, st);
+                    if (rc != WXB_OK) return rc;
+                }
+                CUDA_TRY(cudaEventRecord(c->ev_soft[k], st));
+            }
+            rows_ready = c->ev_soft.data();
+        }
+    }
     // every class's backtrack_kernel and finalize_kernel follow its align_kernel on the same stream, so
     // they overlap the other classes' recurrences instead of running after all of them
     auto finalize = [&](const Bucket &b, cudaStream_t s) -> cudaError_t {
@@ -743,8 +802,8 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
                 for (int ch = cur_chunk; ch < b.chunk; ++ch) { int rc = drain_chunk(ch); if (rc != WXB_OK) return rc; }
                 cur_chunk = b.chunk;
             }
-            if (chunk_ready && seen_chunk[si] < b.chunk) {
-                CUDA_TRY(cudaStreamWaitEvent(c->side[si], chunk_ready[b.chunk], 0));
+            if (rows_ready && seen_chunk[si] < b.chunk) {
+                CUDA_TRY(cudaStreamWaitEvent(c->side[si], rows_ready[b.chunk], 0));
                 seen_chunk[si] = b.chunk;
             }
             CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, c->side[si], debug, pl->has_wild));
@@ -793,7 +852,7 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     ++pl->graph_same;
     if (pl->graph_same < 3) return run_impl(pl, emis, nullptr, o, st, nullptr);      // eager: allocates scratch, configures kernels
     CUDA_TRY(cudaSetDevice(c->device));
-    void *scratch[6] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p};
+    void *scratch[7] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p, c->wide_lp.p};
     if (pl->graph_exec && memcmp(scratch, pl->graph_scratch, sizeof scratch) != 0) {
         cudaGraphExecDestroy(pl->graph_exec);     // a larger plan regrew the shared scratch since the capture
         pl->graph_exec = nullptr;
@@ -817,7 +876,7 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
             pl->graph_off = true;
             return run_impl(pl, emis, nullptr, o, st, nullptr);
         }
-        void *now[6] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p};
+        void *now[7] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p, c->wide_lp.p};
         memcpy(pl->graph_scratch, now, sizeof now);
     }
     pl->last_stream = st;
@@ -1028,17 +1087,7 @@ extern "C" int wxb_log_softmax_device(wxb_ctx *ctx, const float *logits_dev, int
     if (rows < 0 || vocab < 1) return fail(WXB_EINVAL, "wxb_log_softmax_device: bad shape");
     if (rows == 0) return WXB_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const size_t row_bytes = static_cast<size_t>(vocab) * 4;
-    if (row_bytes > static_cast<size_t>(SMEM_LIMIT)) return fail(WXB_EUNSUPPORTED, "wxb_log_softmax_device: vocab %d too large", vocab);
-    int rpc = static_cast<int>(std::min<size_t>(128, (40 * 1024) / row_bytes));
-    if (rpc >= 4) rpc &= ~3;
-    if (rpc < 1) rpc = 1;
-    const size_t smem = static_cast<size_t>(rpc) * row_bytes;
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(log_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const long long blocks = (rows + rpc - 1) / rpc;
-    log_softmax_kernel<<<static_cast<unsigned>(blocks), 128, smem, static_cast<cudaStream_t>(stream)>>>(logits_dev, out_dev, rows, vocab, rpc);
-    CUDA_TRY(cudaGetLastError());
-    return WXB_OK;
+    return launch_log_softmax(logits_dev, out_dev, rows, vocab, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int wxb_backtrack_trellis_device(wxb_ctx *ctx, const float *trellis_dev, const float *emission_dev,

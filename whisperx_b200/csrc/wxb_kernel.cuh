@@ -294,7 +294,20 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             float *tb = reinterpret_cast<float *>(sm + b * L.tile_bytes);
             // ---- kernel (i), fused: log_softmax of the tile rows in place (one row per lane) ----
             if (p.is_logits) {
-                if (lane < n) {
+                if (V > WIDE_V) {                   // wide vocabulary: the warp takes the rows one after another
+                    float mk = 0.0f, lk = 0.0f;
+                    for (int f = 0; f < n; ++f) {
+                        float *row = tb + f * V;
+                        float m, ls;
+                        row_lse_warp(row, V, lane, m, ls);
+                        for (int v = lane; v < V; v += 32) row[v] = logp_from(row[v], m, ls);
+                        if (f == lane) { mk = m; lk = ls; }
+                    }
+                    if (lane < n) {
+                        p.rowmax[d.frame_base + t0 + lane] = mk;
+                        p.rowlse[d.frame_base + t0 + lane] = lk;
+                    }
+                } else if (lane < n) {
                     float *row = tb + lane * V;
                     float m, ls;
                     row_lse([&](int v) { return row[v]; }, V, m, ls);
@@ -325,14 +338,29 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                 __syncwarp();
                 if (t0 + lane < infstart) mine_f = static_cast<float>(mine);
             }
+            float wild_wide = -INFINITY;
+            if (WILD && V > WIDE_V) {               // wide vocabulary: the warp scans the rows one after another
+                for (int f = 0; f < n; ++f) {
+                    float wv = -INFINITY;
+                    for (int v = lane; v < V; v += 32)
+                        if (v != p.blank) wv = fmaxf(wv, tb[f * V + v]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) wv = fmaxf(wv, __shfl_xor_sync(0xffffffffu, wv, o));
+                    if (f == lane) wild_wide = wv;
+                }
+            }
             if (lane < n) {
                 const float ebl = tb[lane * V + p.blank];
                 col0[lane] = mine_f;
                 ebs[lane] = ebl;
                 if (WILD) {
                     float wv = -INFINITY;           // max over the non-blank vocabulary
-                    for (int v = 0; v < V; ++v)
-                        if (v != p.blank) wv = fmaxf(wv, tb[lane * V + v]);
+                    if (V <= WIDE_V) {
+                        for (int v = 0; v < V; ++v)
+                            if (v != p.blank) wv = fmaxf(wv, tb[lane * V + v]);
+                    } else {
+                        wv = wild_wide;
+                    }
                     p.wild[d.frame_base + t0 + lane] = wv;
                     (reinterpret_cast<float *>(sm + L.off_wild) + b * TE)[lane] = wv;
                 }

@@ -214,7 +214,8 @@ __global__ void word_reduce_kernel(long long W, const int *word_seg, const long 
 // Kernel (i) on its own — torch.log_softmax(emissions, dim=-1), alignment.py:233.
 // A CTA stages `rows_per_cta` contiguous rows in shared memory with coalesced (128-bit when
 // aligned) loads, one thread per row runs the same row_lse()/logp_from() as the fused staging,
-// and the tile is written back coalesced.  HBM-bound: 8*V bytes per row.
+// (a warp per row for vocabularies wider than WIDE_V) and the tile is written back coalesced.
+// HBM-bound: 8*V bytes per row.
 __global__ void __launch_bounds__(128) log_softmax_kernel(const float *in, float *out, long long rows, int V,
                                                           int rows_per_cta) {
     extern __shared__ __align__(16) float tile[];
@@ -233,11 +234,21 @@ __global__ void __launch_bounds__(128) log_softmax_kernel(const float *in, float
         for (int i = threadIdx.x; i < nel; i += blockDim.x) tile[i] = __ldg(in + base + i);
     }
     __syncthreads();
-    for (int rr = threadIdx.x; rr < nr; rr += blockDim.x) {
-        float *row = tile + rr * V;
-        float m, ls;
-        row_lse([&](int v) { return row[v]; }, V, m, ls);
-        for (int v = 0; v < V; ++v) row[v] = logp_from(row[v], m, ls);
+    if (V > WIDE_V) {                               // a warp per row (see row_lse_warp)
+        const int lane = threadIdx.x & 31;
+        for (int rr = threadIdx.x >> 5; rr < nr; rr += blockDim.x >> 5) {
+            float *row = tile + rr * V;
+            float m, ls;
+            row_lse_warp(row, V, lane, m, ls);
+            for (int v = lane; v < V; v += 32) row[v] = logp_from(row[v], m, ls);
+        }
+    } else {
+        for (int rr = threadIdx.x; rr < nr; rr += blockDim.x) {
+            float *row = tile + rr * V;
+            float m, ls;
+            row_lse([&](int v) { return row[v]; }, V, m, ls);
+            for (int v = 0; v < V; ++v) row[v] = logp_from(row[v], m, ls);
+        }
     }
     __syncthreads();
     if (vec) {
