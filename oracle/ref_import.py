@@ -84,6 +84,12 @@ def load_reference_diarize():
 
 
 
+def load_reference_utils():
+    """The reference's `whisperx.utils` module (writers, `format_timestamp`), unmodified."""
+    load_reference_alignment()
+    return importlib.import_module("whisperx.utils")
+
+
 def load_reference_alignment():
     """Return the reference's `whisperx.alignment` module (unmodified code)."""
     global _CACHED

@@ -31,6 +31,13 @@ def test_signatures_match_the_live_reference():
     assert wx.alignment.DEFAULT_ALIGN_MODELS_HF == A.DEFAULT_ALIGN_MODELS_HF
     assert tuple(A.LANGUAGES_WITHOUT_SPACES) == tuple(wx.alignment.LANGUAGES_WITHOUT_SPACES)
     assert tuple(A.PUNKT_ABBREVIATIONS) == tuple(wx.alignment.PUNKT_ABBREVIATIONS)
+    U = ref_import.load_reference_utils()
+    for name in ("ResultWriter", "WriteTXT", "SubtitlesWriter", "WriteVTT", "WriteSRT", "WriteTSV", "WriteAudacity", "WriteJSON"):
+        ref_cls, cls = getattr(U, name), getattr(wx.writers, name)
+        assert getattr(ref_cls, "extension", None) == getattr(cls, "extension", None), name
+        assert list(inspect.signature(ref_cls.write_result).parameters) == list(inspect.signature(cls.write_result).parameters), name
+    assert list(inspect.signature(U.get_writer).parameters) == list(inspect.signature(wx.get_writer).parameters)
+    assert list(inspect.signature(U.format_timestamp).parameters) == list(inspect.signature(wx.format_timestamp).parameters)
     D = ref_import.load_reference_diarize()
     assert list(inspect.signature(D.assign_word_speakers).parameters) == list(inspect.signature(wx.assign_word_speakers).parameters)[:3]
 

@@ -13,6 +13,8 @@ from .alignment import (Point, Segment, align, backtrack, get_trellis, load_alig
                         merge_repeats, merge_words, set_sentence_splitter)
 from .diarize import assign_word_speakers  # noqa: F401
 from .engine import AlignEngine, BatchResult, BatchSpec, get_engine  # noqa: F401
+from .writers import format_timestamp, get_writer  # noqa: F401
 
 __all__ = ["load_align_model", "align", "load_audio", "get_trellis", "backtrack", "merge_repeats", "merge_words",
-           "Point", "Segment", "set_sentence_splitter", "assign_word_speakers", "AlignEngine", "BatchSpec", "BatchResult", "get_engine"]
+           "Point", "Segment", "set_sentence_splitter", "assign_word_speakers", "AlignEngine", "BatchSpec", "BatchResult", "get_engine",
+           "get_writer", "format_timestamp"]
