@@ -14,6 +14,7 @@ import pytest
 import torch
 
 from oracle import ref_port
+from whisperx_b200.types import check_aligned_result
 from tests.helpers import DICTIONARY, LABELS, ScriptedModel, regex_spans, same_records
 
 pytestmark = pytest.mark.gpu
@@ -47,6 +48,7 @@ def test_golden_scenarios(wxa, golden_align, capsys):
         d = same_records(res["segments"], m["result"]["segments"], score_tol=0.0010001)
         assert d is None, (name, d)
         assert same_records(res["word_segments"], m["result"]["word_segments"], score_tol=0.0010001) is None
+        check_aligned_result(res, char_alignments=m["return_char_alignments"])
         for t, exp in zip(transcript, m["mutated_inputs"]):
             assert t["clean_char"] == exp["clean_char"] and t["clean_cdx"] == exp["clean_cdx"]
     out = capsys.readouterr().out

@@ -16,6 +16,7 @@ import torch
 from oracle import ref_port
 from tests.helpers import DICTIONARY, regex_spans, same_records
 from whisperx_b200 import _native, assemble
+from whisperx_b200.types import check_aligned_result
 
 
 @pytest.fixture(autouse=True)
@@ -80,6 +81,25 @@ def test_prepare_and_assemble_match_reference(golden_align):
         assert diff is None, (name, diff)
         words = [w for s in segs for w in s["words"]]
         assert same_records(words, m["result"]["word_segments"]) is None, name
+        # the schema (whisperx/types.py:4-58) holds for the reference's dict and for ours
+        check_aligned_result(m["result"], char_alignments=m["return_char_alignments"])
+        check_aligned_result({"segments": segs, "word_segments": words}, char_alignments=m["return_char_alignments"])
+
+
+def test_schema_checker_rejects_malformed_results():
+    good = {"segments": [{"start": 0.0, "end": 1.0, "text": "a b", "words": [{"word": "a", "start": 0.0, "end": 0.5, "score": 0.9}, {"word": "b"}]}]}
+    good["word_segments"] = list(good["segments"][0]["words"])
+    check_aligned_result(good, char_alignments=False)
+    for breakage in (lambda r: r.pop("word_segments"), lambda r: r["segments"][0].pop("words"),
+                     lambda r: r["segments"][0]["words"][0].pop("end"), lambda r: r["segments"][0]["words"][1].update(start=None),
+                     lambda r: r["word_segments"].pop(), lambda r: r["segments"][0]["words"][0].update(score=1)):
+        bad = copy.deepcopy(good)
+        breakage(bad)
+        with pytest.raises(TypeError):
+            check_aligned_result(bad, char_alignments=False)
+    from whisperx_b200 import types as T
+    assert set(T.SingleAlignedSegment.__annotations__) >= {"start", "end", "text", "words", "chars"}
+    assert set(T.AlignedTranscriptionResult.__annotations__) == {"segments", "word_segments"}
 
 
 def test_interpolate_nans_matches_pandas():
