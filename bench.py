@@ -305,8 +305,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "cells_per_s": cells_all / (ms_step * 1e-3),
-            "config": {"workload": "BASELINE configs[1]: 4,096 VAD-cut segments of 5-30 s per GPU, 50 frames/s, vocab 29, "
-                                   "~13.3 chars/s transcripts, raw logits in (fused log-softmax), iid N(0,9) logits",
+            "config": {"workload": WORKLOAD_TEXT[args.workload].format(n=nseg),
                        "segments_per_gpu": nseg, "workload_id": args.workload, "audio_hours_per_gpu": batch.audio_seconds / 3600.0,
                        "cells_per_gpu": int(plan.cells), "emission_bytes_per_gpu": int(host_em.numel() * 4),
                        "l2": f"inputs ({host_em.numel() * 4 / 1e6:.0f} MB per step) larger than L2 (126 MB); no explicit flush",
@@ -335,6 +334,16 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+WORKLOAD_TEXT = {
+    "c2": "BASELINE configs[1]: {n:,} VAD-cut segments of 5-30 s per GPU, 50 frames/s, vocab 29, "
+          "~13.3 chars/s transcripts, raw logits in (fused log-softmax), iid N(0,9) logits",
+    "c5": "profiling workload (BASELINE configs[4] shape): {n:,} segments of 30 s per GPU, 50 frames/s, vocab 29, "
+          "~400-char transcripts, raw logits in (fused log-softmax), iid N(0,9) logits",
+    "c4": "profiling workload (BASELINE configs[3] shape): {n:,} segments of 40-60 s per GPU, vocab 100 (blank = last id), "
+          "500-2,000-char transcripts, raw logits in (log_softmax_kernel, then the recurrence on log-probs), iid N(0,9) logits",
+}
 
 
 def main():

@@ -601,14 +601,40 @@ extern "C" int wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg
 static int launch_log_softmax(const float *in, float *out, int64_t rows, int V, cudaStream_t st) {
     const size_t row_bytes = static_cast<size_t>(V) * 4;
     if (row_bytes > static_cast<size_t>(SMEM_LIMIT)) return fail(WXB_EUNSUPPORTED, "log_softmax: vocab %d too large", V);
-    int rpc = static_cast<int>(std::min<size_t>(128, (40 * 1024) / row_bytes));
-    if (rpc >= 4) rpc &= ~3;
-    if (rpc < 4) rpc = 4;                                   // wide rows: one per warp of the CTA
-    while (rpc > 1 && static_cast<size_t>(rpc) * row_bytes > static_cast<size_t>(SMEM_LIMIT)) --rpc;
-    const size_t smem = static_cast<size_t>(rpc) * row_bytes;
+    // shapes: see log_softmax_kernel
+    if (V > wxb::WIDE_V && V <= 8192) {
+        const int rpc = V <= 1024 ? 8 : 1;
+        const long long need = (rows + rpc - 1) / rpc;
+        const unsigned blocks = static_cast<unsigned>(std::min<long long>(need, 148ll * 8 * 16));
+        if (V <= 128) log_softmax_rows_kernel<4, 1><<<blocks, 256, 0, st>>>(in, out, rows, V);
+        else if (V <= 256) log_softmax_rows_kernel<8, 1><<<blocks, 256, 0, st>>>(in, out, rows, V);
+        else if (V <= 512) log_softmax_rows_kernel<16, 1><<<blocks, 256, 0, st>>>(in, out, rows, V);
+        else if (V <= 1024) log_softmax_rows_kernel<32, 1><<<blocks, 256, 0, st>>>(in, out, rows, V);
+        else if (V <= 2048) log_softmax_rows_kernel<8, 8><<<blocks, 256, 0, st>>>(in, out, rows, V);
+        else if (V <= 4096) log_softmax_rows_kernel<16, 8><<<blocks, 256, 0, st>>>(in, out, rows, V);
+        else log_softmax_rows_kernel<32, 8><<<blocks, 256, 0, st>>>(in, out, rows, V);
+        CUDA_TRY(cudaGetLastError());
+        return WXB_OK;
+    }
+    int rpc, group, pad;
+    if (V <= wxb::WIDE_V) { group = 1; pad = (V & 1) ? 0 : 1; }
+    else { group = 32; pad = 0; }
+    const size_t staged = static_cast<size_t>(V + pad) * 4;
+    if (group == 32) {
+        rpc = static_cast<int>(std::min<size_t>(128, (40 * 1024) / staged));
+        if (rpc >= 4) rpc &= ~3;
+        if (rpc < 4) rpc = 4;                               // one row per warp of the CTA
+        while (rpc > 1 && static_cast<size_t>(rpc) * staged > static_cast<size_t>(SMEM_LIMIT)) --rpc;
+    } else {
+        rpc = static_cast<int>(std::min<size_t>(128, (72 * 1024) / staged));
+        rpc = std::max(rpc & ~3, 4);
+    }
+    const size_t smem = static_cast<size_t>(rpc) * staged;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(log_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // i / V for i < 2^14 as one multiply-high (exact: the error i / 2^32 is far below 1 / V)
+    const unsigned magic = V > 1 ? static_cast<unsigned>((0x100000000ull + static_cast<unsigned>(V) - 1) / static_cast<unsigned>(V)) : 0u;
     const long long blocks = (rows + rpc - 1) / rpc;
-    log_softmax_kernel<<<static_cast<unsigned>(blocks), 128, smem, st>>>(in, out, rows, V, rpc);
+    log_softmax_kernel<<<static_cast<unsigned>(blocks), 128, smem, st>>>(in, out, rows, V, rpc, group, pad, magic);
     CUDA_TRY(cudaGetLastError());
     return WXB_OK;
 }
@@ -642,12 +668,14 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     const bool logits = (pl->flags & WXB_F_LOGITS) != 0;
     if (o->logprobs && !logits) return fail(WXB_EINVAL, "wxb_plan_run: logprobs output is only produced with WXB_F_LOGITS");
     const bool debug = o->trellis || o->final_col;
-    // Wide vocabularies: one producer warp per segment cannot normalise thousands of symbols per frame
-    // at the rate the recurrence consumes them (measured 7.1 ms fused vs 0.38 + 0.27 ms split at
-    // V = 2,304), so the rows go through log_softmax_kernel first — into the caller's logprobs buffer if
-    // there is one, in place when the emissions sit in our own staging buffer (host path), else into
-    // scratch — and the recurrence then runs on log-probs.  Same arithmetic, same bits as the fused way.
-    const bool wide_logits = logits && pl->V > wxb::WIDE_V;
+    // Logits are normalised inside align_kernel (producer warp, one row per lane) only for small odd
+    // vocabularies.  An even V puts the 32 rows of a tile in the same banks (V = 32: the fused C2 batch
+    // takes 1.07 ms instead of 0.33), and one warp cannot normalise thousands of symbols per frame at the
+    // rate the recurrence consumes them (7.1 ms fused vs 0.38 + 0.27 ms split at V = 2,304).  Those batches
+    // go through log_softmax_kernel first — into the caller's logprobs buffer if there is one, in place
+    // when the emissions sit in our own staging buffer (host path), else into scratch — and the
+    // recurrence then runs on log-probs.  Up to V = 64 the arithmetic (and so every bit) is the same.
+    const bool wide_logits = logits && (pl->V > wxb::WIDE_V || (pl->V & 1) == 0);
 
     wxb_ctx *c = pl->ctx;
     CUDA_TRY(cudaSetDevice(c->device));

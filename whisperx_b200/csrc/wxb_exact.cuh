@@ -118,29 +118,32 @@ __device__ __forceinline__ void row_lse(Load x, int V, float &m, float &ls) {
     m = mx;
     ls = logf(s);
 }
-// Rows wider than WIDE_V symbols are reduced by a whole warp (lane l takes symbols l, l+32, ...):
-// shared-memory reads stay conflict-free whatever V is, all 32 lanes work even when a tile holds fewer
-// than 32 frames, and no lane adds thousands of terms into one running sum (the plain serial sum drops
-// every term below half an ulp of it: measured bias 8.5e-6 at V = 7,001).  Lane sums are compensated
-// (Kahan) and combined by a fixed xor tree, so the result is deterministic and the same in the fused
-// producer and in the stand-alone kernel.  All lanes return the same m and ls.
+// Rows wider than WIDE_V symbols are reduced by G lanes together (lane l takes symbols l, l+G, ...):
+// no lane adds thousands of terms into one running sum (the plain serial sum drops every term below
+// half an ulp of it: measured bias 8.5e-6 at V = 7,001).  Lane sums are compensated (Kahan) and
+// combined by a fixed xor tree, so the result is deterministic.  All G lanes return the same m and ls.
+// Every lane of the warp must call it (full-mask shuffles); G = 32 is one row per warp.
 constexpr int WIDE_V = 64;
-__device__ __forceinline__ void row_lse_warp(const float *row, int V, int lane, float &m, float &ls) {
+template <int G>
+__device__ __forceinline__ void row_lse_group(const float *row, int V, int lane_in, float &m, float &ls) {
     float mx = -INFINITY;
-    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, row[v]);
+    for (int v = lane_in; v < V; v += G) mx = fmaxf(mx, row[v]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float s = 0.0f, c = 0.0f;
-    for (int v = lane; v < V; v += 32) {
+    for (int v = lane_in; v < V; v += G) {
         const float y = exp_nonpos(row[v] - mx) - c;
         const float t = s + y;
         c = (t - s) - y;
         s = t;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     m = mx;
     ls = logf(s);
+}
+__device__ __forceinline__ void row_lse_warp(const float *row, int V, int lane, float &m, float &ls) {
+    row_lse_group<32>(row, V, lane, m, ls);
 }
 __device__ __forceinline__ float logp_from(float x, float m, float ls) { return (x - m) - ls; }
 

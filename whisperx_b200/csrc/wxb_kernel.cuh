@@ -294,20 +294,7 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             float *tb = reinterpret_cast<float *>(sm + b * L.tile_bytes);
             // ---- kernel (i), fused: log_softmax of the tile rows in place (one row per lane) ----
             if (p.is_logits) {
-                if (V > WIDE_V) {                   // wide vocabulary: the warp takes the rows one after another
-                    float mk = 0.0f, lk = 0.0f;
-                    for (int f = 0; f < n; ++f) {
-                        float *row = tb + f * V;
-                        float m, ls;
-                        row_lse_warp(row, V, lane, m, ls);
-                        for (int v = lane; v < V; v += 32) row[v] = logp_from(row[v], m, ls);
-                        if (f == lane) { mk = m; lk = ls; }
-                    }
-                    if (lane < n) {
-                        p.rowmax[d.frame_base + t0 + lane] = mk;
-                        p.rowlse[d.frame_base + t0 + lane] = lk;
-                    }
-                } else if (lane < n) {
+                if (lane < n) {         // odd V <= WIDE_V only (conflict-free); other batches are normalised by log_softmax_kernel first
                     float *row = tb + lane * V;
                     float m, ls;
                     row_lse([&](int v) { return row[v]; }, V, m, ls);
@@ -339,7 +326,8 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                 if (t0 + lane < infstart) mine_f = static_cast<float>(mine);
             }
             float wild_wide = -INFINITY;
-            if (WILD && V > WIDE_V) {               // wide vocabulary: the warp scans the rows one after another
+            const bool wild_coop = V > WIDE_V || (V & 1) == 0;      // rows too long for one lane, or all in the same banks
+            if (WILD && wild_coop) {                // the warp scans the rows one after another
                 for (int f = 0; f < n; ++f) {
                     float wv = -INFINITY;
                     for (int v = lane; v < V; v += 32)
@@ -355,7 +343,7 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                 ebs[lane] = ebl;
                 if (WILD) {
                     float wv = -INFINITY;           // max over the non-blank vocabulary
-                    if (V <= WIDE_V) {
+                    if (!wild_coop) {
                         for (int v = 0; v < V; ++v)
                             if (v != p.blank) wv = fmaxf(wv, tb[lane * V + v]);
                     } else {

@@ -211,13 +211,22 @@ __global__ void word_reduce_kernel(long long W, const int *word_seg, const long 
     w_score[w] = round3_np(sum / static_cast<double>(count));   // np.float64.__round__, not Python round
 }
 
-// Kernel (i) on its own — torch.log_softmax(emissions, dim=-1), alignment.py:233.
-// A CTA stages `rows_per_cta` contiguous rows in shared memory with coalesced (128-bit when
-// aligned) loads, one thread per row runs the same row_lse()/logp_from() as the fused staging,
-// (a warp per row for vocabularies wider than WIDE_V) and the tile is written back coalesced.
-// HBM-bound: 8*V bytes per row.
+// Kernel (i) on its own — torch.log_softmax(emissions, dim=-1), alignment.py:233.  HBM-bound: 8*V bytes
+// per row.  Three shapes (launch_log_softmax picks):
+//
+// log_softmax_kernel, group = 1 (V <= 64): a CTA stages `rows_per_cta` contiguous rows in shared memory
+//   with coalesced (128-bit when aligned) loads, one thread per row normalises in the same
+//   row_lse()/logp_from() order as the fused staging, and the tile goes back coalesced.  Rows are staged
+//   with an odd stride (pad = 1 for even V) so that the 32 rows a warp works on start in 32 different
+//   banks — with the plain stride an even V serialises every access (V = 32: 32-way; measured 0.56 vs
+//   5.8 TB/s at V = 29).  The flat index -> staged slot map is i + i / V, the division one multiply-high.
+// log_softmax_rows_kernel<ITER, WPR> (64 < V <= 8192): a warp (V <= 1024) or a whole CTA per row straight
+//   from global memory, the row held in ITER registers per lane — no staging, ITER independent loads in
+//   flight per lane (the staged shape keeps too few bytes in flight once a CTA's tile is tens of KB:
+//   1.7-2.8 TB/s at V = 100-200 against 5.3-6.9 this way).  Lane sums are compensated, then a fixed tree.
+// log_softmax_kernel, group = 32 (wider still): staged, a warp per row (row_lse_warp).
 __global__ void __launch_bounds__(128) log_softmax_kernel(const float *in, float *out, long long rows, int V,
-                                                          int rows_per_cta) {
+                                                          int rows_per_cta, int group, int pad, unsigned magic) {
     extern __shared__ __align__(16) float tile[];
     const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
     const int nr = static_cast<int>(min(static_cast<long long>(rows_per_cta), rows - row0));
@@ -225,39 +234,105 @@ __global__ void __launch_bounds__(128) log_softmax_kernel(const float *in, float
     const long long base = row0 * V;
     const int nel = nr * V;
     const bool vec = ((reinterpret_cast<uintptr_t>(in + base) | reinterpret_cast<uintptr_t>(out + base)) & 15) == 0;
+    const int stride = V + pad;
+    auto slot = [&](int i) { return pad ? i + static_cast<int>(__umulhi(static_cast<unsigned>(i), magic)) * pad : i; };
     if (vec) {
         const float4 *src = reinterpret_cast<const float4 *>(in + base);
-        float4 *t4 = reinterpret_cast<float4 *>(tile);
-        for (int i = threadIdx.x; i < nel / 4; i += blockDim.x) t4[i] = __ldg(src + i);
-        for (int i = (nel & ~3) + threadIdx.x; i < nel; i += blockDim.x) tile[i] = __ldg(in + base + i);
+        if (pad) {
+            for (int i = threadIdx.x; i < nel / 4; i += blockDim.x) {
+                const float4 v = __ldg(src + i);
+                tile[slot(4 * i)] = v.x; tile[slot(4 * i + 1)] = v.y; tile[slot(4 * i + 2)] = v.z; tile[slot(4 * i + 3)] = v.w;
+            }
+        } else {
+            float4 *t4 = reinterpret_cast<float4 *>(tile);
+            for (int i = threadIdx.x; i < nel / 4; i += blockDim.x) t4[i] = __ldg(src + i);
+        }
+        for (int i = (nel & ~3) + threadIdx.x; i < nel; i += blockDim.x) tile[slot(i)] = __ldg(in + base + i);
     } else {
-        for (int i = threadIdx.x; i < nel; i += blockDim.x) tile[i] = __ldg(in + base + i);
+        for (int i = threadIdx.x; i < nel; i += blockDim.x) tile[slot(i)] = __ldg(in + base + i);
     }
     __syncthreads();
-    if (V > WIDE_V) {                               // a warp per row (see row_lse_warp)
-        const int lane = threadIdx.x & 31;
-        for (int rr = threadIdx.x >> 5; rr < nr; rr += blockDim.x >> 5) {
-            float *row = tile + rr * V;
-            float m, ls;
-            row_lse_warp(row, V, lane, m, ls);
-            for (int v = lane; v < V; v += 32) row[v] = logp_from(row[v], m, ls);
-        }
-    } else {
+    if (group == 1) {
         for (int rr = threadIdx.x; rr < nr; rr += blockDim.x) {
-            float *row = tile + rr * V;
+            float *row = tile + rr * stride;
             float m, ls;
             row_lse([&](int v) { return row[v]; }, V, m, ls);
             for (int v = 0; v < V; ++v) row[v] = logp_from(row[v], m, ls);
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        for (int rr = threadIdx.x >> 5; rr < nr; rr += blockDim.x >> 5) {
+            float *row = tile + rr * stride;
+            float m, ls;
+            row_lse_warp(row, V, lane, m, ls);
+            for (int v = lane; v < V; v += 32) row[v] = logp_from(row[v], m, ls);
         }
     }
     __syncthreads();
     if (vec) {
         float4 *dst = reinterpret_cast<float4 *>(out + base);
-        const float4 *t4 = reinterpret_cast<const float4 *>(tile);
-        for (int i = threadIdx.x; i < nel / 4; i += blockDim.x) dst[i] = t4[i];
-        for (int i = (nel & ~3) + threadIdx.x; i < nel; i += blockDim.x) out[base + i] = tile[i];
+        if (pad) {
+            for (int i = threadIdx.x; i < nel / 4; i += blockDim.x)
+                dst[i] = make_float4(tile[slot(4 * i)], tile[slot(4 * i + 1)], tile[slot(4 * i + 2)], tile[slot(4 * i + 3)]);
+        } else {
+            const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+            for (int i = threadIdx.x; i < nel / 4; i += blockDim.x) dst[i] = t4[i];
+        }
+        for (int i = (nel & ~3) + threadIdx.x; i < nel; i += blockDim.x) out[base + i] = tile[slot(i)];
     } else {
-        for (int i = threadIdx.x; i < nel; i += blockDim.x) out[base + i] = tile[i];
+        for (int i = threadIdx.x; i < nel; i += blockDim.x) out[base + i] = tile[slot(i)];
+    }
+}
+
+template <int ITER, int WPR>      // WPR warps per row: 1 (a row per warp, 8 rows per CTA) or 8 (a row per CTA)
+__global__ void __launch_bounds__(256) log_softmax_rows_kernel(const float *in, float *out, long long rows, int V) {
+    static_assert(WPR == 1 || WPR == 8, "one warp or the whole CTA per row");
+    __shared__ float red[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int RPC = 8 / WPR, CS = 32 * WPR;
+    const int col = (warp % WPR) * 32 + lane;
+    const long long step = static_cast<long long>(gridDim.x) * RPC;
+    for (long long row = static_cast<long long>(blockIdx.x) * RPC + warp / WPR; row < rows; row += step) {
+        const float *src = in + row * V;
+        float x[ITER];
+#pragma unroll
+        for (int k = 0; k < ITER; ++k) x[k] = (col + CS * k < V) ? __ldg(src + col + CS * k) : -INFINITY;
+        float mx = x[0];
+#pragma unroll
+        for (int k = 1; k < ITER; ++k) mx = fmaxf(mx, x[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if constexpr (WPR == 8) {
+            if (lane == 0) red[0][warp] = mx;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[0][w]);
+        }
+        float s = 0.0f, c = 0.0f;           // WPR == 1: the order of row_lse_group<32>
+#pragma unroll
+        for (int k = 0; k < ITER; ++k) {
+            if (col + CS * k < V) {
+                const float y = exp_nonpos(x[k] - mx) - c;
+                const float t = s + y;
+                c = (t - s) - y;
+                s = t;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if constexpr (WPR == 8) {
+            if (lane == 0) red[1][warp] = s;
+            __syncthreads();
+            s = red[1][0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) s += red[1][w];
+        }
+        const float ls = logf(s);
+        float *dst = out + row * V;
+#pragma unroll
+        for (int k = 0; k < ITER; ++k)
+            if (col + CS * k < V) dst[col + CS * k] = logp_from(x[k], mx, ls);
+        if constexpr (WPR == 8) __syncthreads();      // red[] is reused by the next row
     }
 }
 
