@@ -61,7 +61,7 @@ def check_against_oracle(spec, res, cases, blank, full=True):
                 assert np.array_equal(pl[on].view(np.int32), p["logp"].view(np.int32))   # bit-exact log-probs
 
 
-@pytest.mark.parametrize("V,blank,align", [(29, 0, 1), (29, 0, 4), (29, 7, 4), (100, 99, 1), (100, 99, 4), (5, 2, 1), (2, 1, 4)])
+@pytest.mark.parametrize("V,blank,align", [(29, 0, 1), (29, 0, 4), (29, 7, 4), (100, 99, 1), (100, 99, 4), (5, 2, 1), (2, 1, 4), (32, 0, 1), (64, 63, 4)])
 def test_random_segments_bit_exact(engine, V, blank, align):
     rng = np.random.default_rng(100 + V + align)
     cases = []
@@ -187,7 +187,7 @@ def test_logits_mode_is_path_exact_on_own_logprobs(engine):
     """Fused log-softmax: feeding the engine's own log-probs to the oracle DP reproduces its paths
     exactly, and those log-probs are within 2 ulp-ish of torch's (SURVEY §7.2 hard part 1)."""
     rng = np.random.default_rng(21)
-    for V, blank in ((29, 0), (100, 99), (33, 4)):
+    for V, blank in ((29, 0), (100, 99), (33, 4), (32, 0), (48, 47), (64, 1), (1, 0), (2, 0)):   # odd <= 64: fused; others: split
         raw, toks = [], []
         for c in range(60):
             T = int(rng.integers(2, 300)); N = int(rng.integers(1, T + 1))
@@ -208,6 +208,10 @@ def test_logits_mode_is_path_exact_on_own_logprobs(engine):
                 cases.append((mine.copy(), toks[s]))
             spec2 = BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank)
             check_against_oracle(spec2, res, cases, blank, full=False)
+            # normalising first and aligning the log-probs gives the fused call's bytes (V <= 64: same arithmetic)
+            two_step = engine.align_batch(torch.from_numpy(alone).cuda(), spec2, want=("path",)).cpu()
+            for f in ("status", "n_frames", "char_start", "char_end", "char_score"):
+                assert torch.equal(getattr(res, f).view(torch.uint8), getattr(two_step, f).view(torch.uint8)), (V, f)
             # path log-probs are taken from the same values
             for s, (mine, tk) in enumerate(cases):
                 p = c_oracle.walk_back(c_oracle.forward_trellis(mine, tk, blank), mine, tk, blank)
@@ -380,7 +384,7 @@ def test_repeated_runs_are_bitwise_identical(engine):
     plan.close()
 
 
-@pytest.mark.parametrize("V,blank", [(29, 0), (100, 99), (7, 3)])
+@pytest.mark.parametrize("V,blank", [(29, 0), (100, 99), (7, 3), (32, 0)])
 def test_wildcard_tokens_extension(engine, V, blank):
     """EXTENSION (not in the reference fork; parity unpinned by the reference): token id -1 is
     a wildcard whose emission is the best non-blank log-prob of the frame.  Checked against the oracle's
