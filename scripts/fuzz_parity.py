@@ -27,7 +27,7 @@ def main():
     t_end = time.time() + args.seconds
     batches = segs = cells = 0
     while time.time() < t_end:
-        V = int(rng.choice([2, 5, 29, 29, 29, 33, 64, 100, 131]))
+        V = int(rng.choice([1, 2, 5, 29, 29, 29, 32, 32, 33, 48, 64, 100, 131, 300, 1100]))
         blank = int(rng.integers(0, V))
         wildcard = bool(rng.random() < 0.3)
         logits = bool(rng.random() < 0.5)
