@@ -45,6 +45,10 @@ extern "C" {
 #define WXB_F_WILDCARD      4u   /* EXTENSION (not in the reference fork): token id -1 is a wildcard whose emission at
                                     frame t is max over non-blank v of logp[t, v]; its path probability is exp of that */
 
+#define WXB_F_CLOBBER       8u   /* the emission buffer is the caller's scratch: the engine may overwrite it (with
+                                    WXB_F_LOGITS, batches that are normalised before the recurrence are then
+                                    normalised in place instead of into a copy; run such a plan once per buffer) */
+
 typedef struct wxb_ctx wxb_ctx;     /* per-device workspace (scratch buffers, side streams) */
 typedef struct wxb_plan wxb_plan;   /* a batch description uploaded and bucketed once, runnable many times */
 

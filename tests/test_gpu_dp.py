@@ -515,8 +515,13 @@ def test_wide_vocabularies_shorten_the_tiles(engine, V, blank):
         host2 = engine.align_batch_host(E, spec, want=("path",))
     finally:
         engine._lib.wxb_set_chunk_bytes(engine._ctx, old)
+    # WXB_F_CLOBBER: the caller's buffer is scratch, the rows are normalised in place (no copy)
+    scratch = Ed.clone()
+    spec_c = BatchSpec(frame_off=fo, frame_len=fl, tok_off=to, tokens=tok, vocab=V, blank_id=blank, logits=True, no_shortcut=True, clobber=True)
+    inplace = engine.align_batch(scratch, spec_c, want=("path",)).cpu()
+    assert torch.equal(scratch.cpu().view(torch.int32), res.logprobs.view(-1, V).view(torch.int32))
     for f in ("status", "n_frames", "char_start", "char_end", "char_score", "path_token", "path_logp"):
-        for other in (again, host, host2):
+        for other in (again, host, host2, inplace):
             assert torch.equal(getattr(res, f).view(torch.uint8), getattr(other, f).view(torch.uint8)), f
     assert torch.equal(res.logprobs.view(torch.int32), host.logprobs.view(torch.int32))
 

@@ -17,6 +17,7 @@ SEG_FAILED = 1
 F_LOGITS = 1
 F_NO_SHORTCUT = 2
 F_WILDCARD = 4
+F_CLOBBER = 8
 
 i32p = C.POINTER(C.c_int32)
 i64p = C.POINTER(C.c_int64)

@@ -311,7 +311,7 @@ def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], d
     has_words = len(wchar_off) > 1
     spec = BatchSpec(frame_off=frame_off, frame_len=frame_len, tok_off=tok_off, tokens=np.asarray(tokens, np.int32),
                      vocab=V, blank_id=blank, logits=fused, wildcard=(-1 in tokens), seg_t1=t1, seg_ratio=ratio,
-                     seg_round_np=round_np,
+                     seg_round_np=round_np, clobber=(fused and not KEEP_LAST_BATCH),      # emis is our own concatenation
                      word_off=word_off if has_words else None,
                      wchar_off=np.asarray(wchar_off, np.int64) if has_words else None,
                      wchar_idx=np.asarray(wchar_idx, np.int32) if has_words else None)

@@ -685,7 +685,7 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     float *wide_dst = nullptr;
     if (wide_logits) {
         if (o->logprobs) wide_dst = o->logprobs;
-        else if (chunk_ready) wide_dst = const_cast<float *>(emis);       // c->h_emis, ours
+        else if (chunk_ready || (pl->flags & WXB_F_CLOBBER)) wide_dst = const_cast<float *>(emis);   // c->h_emis (ours), or the caller's scratch
         else {
             CUDA_TRY(c->wide_lp.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * pl->V * 4));
             wide_dst = c->wide_lp.as<float>();
@@ -868,7 +868,7 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
     wxb_ctx *c = pl->ctx;
-    if (elapsed_dp_ms || !c->use_graphs || c->want_trace || pl->graph_off || pl->S == 0)
+    if (elapsed_dp_ms || !c->use_graphs || c->want_trace || pl->graph_off || pl->S == 0 || (pl->flags & WXB_F_CLOBBER))
         return run_impl(pl, emis, nullptr, o, st, elapsed_dp_ms);
     const bool same = pl->graph_emis == emis && memcmp(&pl->graph_out, o, sizeof(wxb_outputs)) == 0;
     if (!same) {

@@ -36,6 +36,7 @@ class BatchSpec:
     logits: bool = False             # emissions are raw logits -> fused log_softmax
     no_shortcut: bool = False
     wildcard: bool = False           # extension: token id -1 = wildcard (max over the non-blank vocabulary)
+    clobber: bool = False            # the emission buffer is scratch: logits may be normalised in place
     seg_t1: Optional[np.ndarray] = None      # float64 [S]
     seg_ratio: Optional[np.ndarray] = None   # float64 [S]
     seg_round_np: Optional[np.ndarray] = None  # uint8 [S]: numpy-typed segment times (numpy rounding)
@@ -91,7 +92,7 @@ class BatchSpec:
         b.vocab = int(self.vocab)
         b.blank_id = int(self.blank_id)
         b.flags = ((N.F_LOGITS if self.logits else 0) | (N.F_NO_SHORTCUT if self.no_shortcut else 0)
-                   | (N.F_WILDCARD if self.wildcard else 0))
+                   | (N.F_WILDCARD if self.wildcard else 0) | (N.F_CLOBBER if self.clobber else 0))
         b.frame_off = _ptr(self.frame_off, C.c_int64)
         b.frame_len = _ptr(self.frame_len, C.c_int32)
         b.tok_off = _ptr(self.tok_off, C.c_int64)
