@@ -206,3 +206,57 @@ def test_wildcard_extension_end_to_end(wxa):
     # off (default): identical to the reference behaviour — the digits get no timestamps
     plain = wxa.align(copy.deepcopy(transcript), ScriptedModel(logps, "cuda:0"), meta, audio, "cuda:0")
     assert "start" not in {w["word"]: w for w in plain["word_segments"]}["2014"]
+
+
+class _HFStyle(torch.nn.Module):
+    """A HuggingFace-shaped CTC model: forward(waveform) -> object with `.logits` [1, T, V] (alignment.py:229-230)."""
+
+    def __init__(self, vocab):
+        super().__init__()
+        import torchaudio
+        torch.manual_seed(1)
+        params = dict(torchaudio.pipelines.WAV2VEC2_ASR_BASE_960H._params, aux_num_out=vocab)
+        self.net = torchaudio.models.wav2vec2_model(**params).eval()
+
+    def forward(self, waveform):
+        from types import SimpleNamespace
+        return SimpleNamespace(logits=self.net(waveform)[0])
+
+
+@pytest.mark.parametrize("mode", ["fused", "torch"])
+def test_huggingface_style_model_with_a_32_symbol_head(wxa, mode):
+    """Typical HF wav2vec2 CTC head: 32 symbols, '<pad>' (the blank, alignment.py:237-240) at id 0, '|' word
+    separator.  An even vocabulary takes the normalise-first route inside the engine; results must be the
+    reference algorithm's on the engine's own log-probs."""
+    specials = ["<pad>", "<s>", "</s>", "<unk>", "|"]
+    vocab = {tok: i for i, tok in enumerate(specials + list("abcdefghijklmnopqrstuvwxyz") + ["'"])}
+    assert len(vocab) == 32
+    model = _HFStyle(32).to("cuda:0")
+    meta = {"language": "en", "dictionary": vocab, "type": "huggingface"}
+    g = torch.Generator().manual_seed(9)
+    audio = (torch.randn(12 * 16000, generator=g) * 0.1).numpy()
+    wxa.EMISSION_MODE = mode
+    wxa.KEEP_LAST_BATCH = True
+    ours = wxa.align(copy.deepcopy(TRANSCRIPT), model, meta, audio, "cuda:0", return_char_alignments=True)
+    last = wxa.LAST_BATCH
+    spec = last["spec"]
+    assert spec.vocab == 32 and spec.blank_id == 0
+    lp = (last["result"].logprobs if mode == "fused" else last["emissions"]).view(-1, 32).cpu()
+
+    def engine_logprobs(k, emission, _n=[0]):
+        i = _n[0]; _n[0] += 1
+        a, T = int(spec.frame_off[i]), int(spec.frame_len[i])
+        if int(spec.tok_off[i + 1] - spec.tok_off[i]) > T:
+            return None
+        torch.testing.assert_close(lp[a:a + T], emission, rtol=0, atol=0 if mode == "torch" else 2e-5)
+        return lp[a:a + T]
+
+    ref = ref_port.align_port(copy.deepcopy(TRANSCRIPT), model, meta, audio, "cuda:0", return_char_alignments=True,
+                              span_fn=regex_spans, emission_hook=engine_logprobs)
+    d = same_records(ours["segments"], ref["segments"], score_tol=0.0010001)
+    assert d is None, d
+    assert same_records(ours["word_segments"], ref["word_segments"], score_tol=0.0010001) is None
+    check_aligned_result(ours, char_alignments=True)
+    wxa.KEEP_LAST_BATCH = False
+    again = wxa.align(copy.deepcopy(TRANSCRIPT), model, meta, audio, "cuda:0", return_char_alignments=True)   # in-place route
+    assert same_records(again["segments"], ours["segments"]) is None
