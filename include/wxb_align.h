@@ -139,7 +139,10 @@ int  wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg_bytes, in
  * to void*; NULL = legacy default stream) and the call returns without synchronising.
  * `elapsed_dp_ms`, if not NULL, makes the call synchronise and report the CUDA-event time of
  * the DP kernels alone.  Calls that repeat the same (emissions, outputs) pointers are replayed as a
- * CUDA graph from the third one on (WXB_GRAPHS=0 disables). */
+ * CUDA graph from the third one on (WXB_GRAPHS=0 disables).
+ * All plans of a ctx share its scratch buffers and side streams: a run waits (on the device, through an event)
+ * for the previous run of the same ctx, whatever stream that was enqueued on, so runs of one ctx never overlap.
+ * Calls into one ctx must come from one host thread at a time; use one ctx per thread / per GPU for concurrency. */
 int  wxb_plan_run(wxb_plan *plan, const float *emissions_dev, const wxb_outputs *out_dev,
                   void *stream, float *elapsed_dp_ms);
 
@@ -175,7 +178,9 @@ int  wxb_backtrack_trellis_device(wxb_ctx *ctx, const float *trellis_dev, const 
  *   rows with intersection_d > 0 only, unless fill_nearest                (:42-45, :55-58)
  *   per-speaker sums in row order (pandas groupby-sum: Kahan compensated), arg-max, ties to the
  *   lowest speaker id (ids must follow the sorted label order, as groupby does)   (:47-48, :60-61)
- * out_speaker[q] = speaker id, or -1 when no row qualifies.  n_speakers <= 64.
+ * out_speaker[q] = speaker id, or -1 when no row qualifies.  Any n_speakers (64 per launch; more are covered by
+ * successive launches that carry the running winner).  Ids outside [0, n_speakers) are ignored by the device entry
+ * point and rejected (WXB_EINVAL) by the host one.
  * _device: all pointers are device memory, work is enqueued on `stream`; _host: host pointers, blocking. */
 int  wxb_assign_speakers_device(wxb_ctx *ctx, const double *diar_start, const double *diar_end,
                                 const int32_t *diar_speaker, int64_t n_diar, int32_t n_speakers,
@@ -190,6 +195,21 @@ int  wxb_assign_speakers_host(wxb_ctx *ctx, const double *diar_start, const doub
  * rows: [cap_rows][8] = {t_begin_ns, t_forward_done_ns, t_end_ns, smid, T, N, K, segment}; returns the
  * number of rows written or a negative error code. */
 int  wxb_plan_debug_trace(wxb_plan *plan, uint64_t *rows, int64_t cap_rows);
+
+/* ---- exact scores on the host (alignment.py:409, :444, :264, :308) ----
+ * The reference's point probability is `emission[t, idx].exp().item()` on a CPU tensor (:409), i.e. whatever exp
+ * the host's torch build dispatches to (MKL VML here: its float32 results differ between the AVX2 and AVX-512 code
+ * paths in ~4 % of the values, profiles/r2_exp_host_dependence.md) — no fixed device formula can reproduce it on
+ * every host.  A caller that needs the dict's `score` fields byte-identical to the reference run on the same
+ * machine asks wxb_plan_run for path_logp (bit-exact float32), applies its own exp to it (the Python side calls
+ * torch.exp on the host, the very op the reference calls) and hands the probabilities to this function, which
+ * redoes the three reductions in the reference's order: per character the Python-order float64 sum / count
+ * (:444), round(score, 3) (:264), and per word round(mean of rounded char scores, 3) in numpy's pairwise order
+ * (:308).  All pointers are HOST memory; `batch` is the description the plan was made from (frame_off, tok_off and,
+ * for word_score, the word groups).  char_score_r / word_score may be NULL.  No GPU work, no ctx. */
+int  wxb_exact_scores_host(const wxb_batch *batch, const float *path_prob, const int32_t *status,
+                           const int32_t *char_start, const int32_t *char_end,
+                           double *char_score, double *char_score_r, double *word_score);
 
 /* ---- host-side exact helpers (no GPU needed; the device code uses the same source) ---- */
 double wxb_round3(double x);                              /* Python round(x, 3) (alignment.py:262-264) */

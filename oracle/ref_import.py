@@ -18,11 +18,30 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("WXB_REFERENCE_ROOT", "/root/reference")
+# /root/reference exists in the build container only.  `python -m oracle.make_ref` (run by
+# __graft_entry__.build()) copies the files this importer executes into the git-ignored oracle/_ref/,
+# which travels to the GPU box with the snapshot: there the reference is imported from that copy.
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = (os.environ.get("WXB_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref"))
+
+
+def _find_root() -> str:
+    for root in _CANDIDATES:
+        if root and os.path.isfile(os.path.join(root, "whisperx", "alignment.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "whisperx", "alignment.py"))
+
+
+def reference_is_live_checkout() -> bool:
+    """True when the importer runs the files where they lie under /root/reference (not the build-time copy)."""
+    return reference_available() and os.path.abspath(REFERENCE_ROOT) != os.path.join(_HERE, "_ref")
 
 
 # The splitter both sides of a parity test share.  Signature: text -> list[(start, end)].

@@ -17,12 +17,11 @@ from oracle import c_oracle
 from whisperx_b200.engine import BatchSpec, get_engine
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--seconds", type=float, default=120.0)
-    ap.add_argument("--seed", type=int, default=0)
-    args = ap.parse_args()
-    eng = get_engine("cuda:0")
+def fuzz(seconds: float, seed: int, eng=None):
+    """Runs random batches for `seconds`; returns (batches, segments, cells).  Raises on the first difference."""
+    import types
+    args = types.SimpleNamespace(seconds=seconds, seed=seed)
+    eng = eng or get_engine("cuda:0")
     rng = np.random.default_rng(args.seed)
     t_end = time.time() + args.seconds
     batches = segs = cells = 0
@@ -77,6 +76,15 @@ def main():
             cells += T * (sl.stop - sl.start)
         batches += 1
         segs += S
+    return batches, segs, cells
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120.0)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    batches, segs, cells = fuzz(args.seconds, args.seed)
     print(f"fuzz ok: {batches} batches, {segs} segments, {cells/1e6:.1f} Mcells, seed {args.seed}")
 
 

@@ -89,3 +89,11 @@ def same_records(got, exp, score_tol=0.0):
             elif g[k] != e[k]:
                 return f"record {i}: {k} {g[k]!r} != {e[k]!r}"
     return None
+
+
+def host_exp_matches_fixtures() -> bool:
+    """True when this machine's torch CPU exp reproduces tests/golden/exp_canary.npz, i.e. runs the same MKL code
+    path as the container that generated the golden `score` fields (scripts/make_golden_exp_canary.py)."""
+    import os
+    c = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exp_canary.npz"))
+    return bool(np.array_equal(torch.exp(torch.from_numpy(c["x"])).numpy().view(np.int32), c["y"].view(np.int32)))

@@ -58,7 +58,7 @@ SYMBOLS = (
     "wxb_plan_run", "wxb_plan_debug_trace", "wxb_align_device", "wxb_align_host", "wxb_log_softmax_device",
     "wxb_backtrack_trellis_device", "wxb_round3", "wxb_round3_np", "wxb_pairwise_sum", "wxb_tokens_per_lane",
     "wxb_segment_warps", "wxb_set_k_target", "wxb_assign_speakers_device", "wxb_assign_speakers_host",
-    "wxb_set_chunk_bytes",
+    "wxb_set_chunk_bytes", "wxb_exact_scores_host",
 )
 
 _LIB = None
@@ -110,6 +110,8 @@ def load(build_if_missing: bool = True):
     L.wxb_assign_speakers_host.restype = C.c_int
     L.wxb_set_chunk_bytes.argtypes = [vp, C.c_int64]
     L.wxb_set_chunk_bytes.restype = C.c_int64
+    L.wxb_exact_scores_host.argtypes = [C.POINTER(Batch), vp, vp, vp, vp, vp, vp, vp]
+    L.wxb_exact_scores_host.restype = C.c_int
     L.wxb_set_k_target.argtypes = [C.c_int]
     L.wxb_set_k_target.restype = C.c_int
     for name in ("wxb_create", "wxb_get_limits", "wxb_plan_create", "wxb_plan_launch_count", "wxb_plan_stats",

@@ -60,11 +60,22 @@ DEFAULT_ALIGN_MODELS_HF = {               # alignment.py:32-61
 }
 
 # How emissions reach the kernels:
-#   "fused"  raw logits go in and log_softmax(dim=-1) happens while a tile is staged (default)
-#   "torch"  torch.log_softmax on the device first (the op the reference calls at alignment.py:233),
-#            then the kernels take log-probs
+#   "torch"  torch.log_softmax on the device first — the very op the reference calls at alignment.py:233 on
+#            the model's device — then the kernels take log-probs.  Default: with device="cuda" the reference
+#            feeds its DP exactly these floats, so paths, frames and timestamps are the reference's bit for bit.
+#   "fused"  raw logits go in and log_softmax(dim=-1) happens while a tile is staged (the batch C ABI's
+#            WXB_F_LOGITS; saves one pass over the emissions).  The engine's log-probs differ from torch's by
+#            up to ~2e-5, which can flip a near-tie of the float32 trellis: measured divergence from the
+#            reference in profiles/r2_divergence.md.  Bit-exact *given identical log-probs*.
 #   "logprobs" the model's output already is log-probabilities; nothing is applied
-EMISSION_MODE = os.environ.get("WXB_EMISSION_MODE", "fused")
+EMISSION_MODE = os.environ.get("WXB_EMISSION_MODE", "torch")
+# The reference's point probability is `emission[t, c].exp().item()` on a CPU tensor (alignment.py:409): the host
+# torch's exp, whose float32 results depend on the host's instruction set (MKL VML; profiles/r2_exp_host_dependence.md).
+# True (default): align() reads the path's log-probs back (bit-exact float32), applies torch.exp on the host — the
+# same call, on the same machine, as the reference — and redoes the score reductions in the reference's order
+# (wxb_exact_scores_host): every `score` of the returned dict is byte-identical to the reference's.
+# False: scores come from the kernels (CUDA expf: <= 1e-6 relative, rounded values may differ by 0.001).
+EXACT_SCORES = os.environ.get("WXB_EXACT_SCORES", "1") not in ("", "0")
 # >1: segments with the same number of samples share one wav2vec2 forward;
 # 1 keeps the reference's batch-1 forwards (alignment.py:215 has this as a TODO).
 EMISSION_BATCH = int(os.environ.get("WXB_EMISSION_BATCH", "1"))
@@ -315,7 +326,8 @@ def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], d
                      word_off=word_off if has_words else None,
                      wchar_off=np.asarray(wchar_off, np.int64) if has_words else None,
                      wchar_idx=np.asarray(wchar_idx, np.int32) if has_words else None)
-    res = engine.align_batch(emis, spec, want=("logprobs",) if (KEEP_LAST_BATCH and fused) else ())
+    want = (("logprobs",) if (KEEP_LAST_BATCH and fused) else ()) + (("path",) if EXACT_SCORES else ())
+    res = engine.align_batch(emis, spec, want=want)
     if KEEP_LAST_BATCH:
         LAST_BATCH.clear()
         LAST_BATCH.update(spec=spec, result=res, emissions=emis)
@@ -327,6 +339,9 @@ def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], d
         ws, we, wsc = res.word_start_s.cpu().tolist(), res.word_end_s.cpu().tolist(), res.word_score.cpu().tolist()
     else:
         ws = we = wsc = []
+    if EXACT_SCORES:
+        sc, exact_w = exact_scores(engine, spec, res)
+        wsc = exact_w if has_words else wsc
     out = []
     for s in range(S):
         if status[s] != 0:
@@ -336,6 +351,24 @@ def _align_batch(engine, segs: Sequence[dict], logits: Sequence[torch.Tensor], d
         g0, g1 = int(word_off[s]), int(word_off[s + 1])
         out.append((layouts[s], cs[a:b], ce[a:b], sc[a:b], ws[g0:g1], we[g0:g1], wsc[g0:g1]))
     return {"segments": out, "spec": spec, "result": res}
+
+
+def exact_scores(engine, spec: BatchSpec, res):
+    """Scores of a batch with the host's own exp (see EXACT_SCORES).  -> (char_score_r list, word_score list)."""
+    import ctypes as C
+    from . import _native as N
+    prob = torch.exp(res.path_logp.cpu()).contiguous()              # alignment.py:409, the reference's own op
+    status = res.status.cpu().contiguous()
+    c0, c1 = res.char_start.cpu().contiguous(), res.char_end.cpu().contiguous()
+    n_chars, n_words = max(spec.sum_N, 1), max(spec.n_words, 1)
+    score = np.empty(n_chars, np.float64)
+    score_r = np.empty(n_chars, np.float64)
+    wscore = np.empty(n_words, np.float64)
+    cb = spec.to_c()
+    N.check(engine._lib.wxb_exact_scores_host(C.byref(cb), prob.data_ptr(), status.data_ptr(), c0.data_ptr(), c1.data_ptr(),
+                                              score.ctypes.data, score_r.ctypes.data,
+                                              wscore.ctypes.data if spec.n_words > 0 else None), "wxb_exact_scores_host")
+    return score_r.tolist(), wscore.tolist()
 
 
 # --------------------------------------------------------------------------- functional API

@@ -8,6 +8,8 @@
 #include "wxb_small.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -98,16 +100,22 @@ struct wxb_ctx {
     cudaStream_t copy = nullptr;              // host->device emission chunks (wxb_align_host)
     cudaStream_t d2h = nullptr;               // per-chunk word reduction + device->host result copies (wxb_align_host)
     cudaEvent_t ev_d2h = nullptr;
+    cudaEvent_t ev_busy = nullptr;            // end of the last wxb_plan_run of this ctx (runs share the scratch)
+    cudaStream_t last_run_stream = nullptr;
     cudaEvent_t ev_dbg[3] = {};               // WXB_DEBUG_TIMING: kernels joined / results on the host / per-chunk
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<cudaEvent_t> ev_chunk;        // one per emission chunk in flight
     std::vector<cudaEvent_t> ev_soft;         // wide-vocabulary logits: chunk normalised
-    DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, trace, wide_lp;
+    DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, trace, wide_lp, spk_best;
     int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
+    int k_target = 0;                         // WXB_K_TARGET / wxb_ctx_set_k_target: 0 = process default, then per batch
+    int tile_pref = 32;                       // WXB_TILE_FRAMES (experiments): largest tile length tried
+    int ring_extra = 2;                       // WXB_RING_EXTRA (experiments): ring depth = W + this
     bool want_trace = false;                  // WXB_TRACE=1
     bool use_graphs = true;                   // WXB_GRAPHS=0 disables graph replay in wxb_plan_run
     size_t chunk_bytes = 64u << 20;           // WXB_CHUNK_MB: emission bytes per pipelined H2D chunk
+    bool chunk_taper = true;                  // WXB_CHUNK_TAPER=0: no tapered tail (see make_chunk_bounds)
     std::vector<Arena *> arena_pool;          // metadata arenas of destroyed plans, ready for reuse
     // wxb_align_host staging
     DevBuf h_emis, h_i32[4], h_f64[7], h_path_tok, h_f32[4];
@@ -146,7 +154,9 @@ struct wxb_plan {
 
 // Warps and tokens-per-lane for a transcript of n tokens: as few compute warps as keep K <= k_target
 // (more columns per lane amortise the per-frame overhead; more warps shorten the segment's latency).
-static int g_k_target = 0;        // 0 = chosen per batch (see pick_k_target); 1..KMAX = forced
+// Process-wide *default* only (wxb_set_k_target, atomic): a plan uses its ctx's own k_target (WXB_K_TARGET at
+// wxb_create) and falls back to this one, so contexts on different devices / threads share no mutable planner state.
+static std::atomic<int> g_k_target{0};        // 0 = chosen per batch (see pick_k_target); 1..KMAX = forced
 
 // Few columns per lane (more warps per segment) shorten a segment's latency, which is what bounds a
 // batch whose longest segments are a large part of the makespan; many columns per lane spend fewer
@@ -175,7 +185,7 @@ static int pick_k_target(const int64_t *tok_off, const int64_t *frame_off, const
 
 static bool shape_of(long long n, int *W, int *K, int k_target = 0) {
     if (n <= 0) return false;
-    if (k_target <= 0) k_target = g_k_target > 0 ? g_k_target : 5;
+    if (k_target <= 0) { const int g = g_k_target.load(std::memory_order_relaxed); k_target = g > 0 ? g : 5; }
     long long w = (n + 32ll * k_target - 1) / (32ll * k_target);
     if (w > WMAX) w = WMAX;
     const long long k = (n + 32 * w - 1) / (32 * w);
@@ -193,8 +203,7 @@ static int tokens_per_lane(long long n) {
 
 // Frames per shared-memory tile (cp.async.bulk needs 16-byte multiples, i.e. TE % 4 == 0): 32 when the
 // widest CTA of the batch still fits a ring of at least 2 tiles, else 16, 8, 4.
-static int g_tile_pref = 32;     // WXB_TILE_FRAMES (experiments): largest tile length tried
-static int g_ring_extra = 2;     // WXB_RING_EXTRA (experiments): ring depth = W + this
+// (tile_pref = WXB_TILE_FRAMES, ring_extra = WXB_RING_EXTRA: per-ctx experiment knobs, defaults 32 and 2)
 
 // Tile length (frames) and ring depth of a W-warp CTA over a V-wide vocabulary.  32-frame tiles
 // amortise the per-tile hand-offs best (measured: 16 costs +25 % on the V=29 benchmark), so they are
@@ -202,18 +211,18 @@ static int g_ring_extra = 2;     // WXB_RING_EXTRA (experiments): ring depth = W
 // with many warps); the ring is W+2 deep — every warp on its own tile plus one being filled — or
 // shallower if shared memory says so (any depth >= 2 is deadlock-free).  cp.async.bulk needs
 // 16-byte multiples, i.e. TE % 4 == 0.
-static int pick_shape(int W, int V, bool wild, int *TE, int *NB, size_t *smem) {
+static int pick_shape(int tile_pref, int ring_extra, int W, int V, bool wild, int *TE, int *NB, size_t *smem) {
     const int pref[4] = {32, 16, 8, 4};
     const int want_ctas = std::max(1, (16 + W) / (W + 1));
     int chosen = -1;
     for (int i = 0; i < 4 && chosen < 0; ++i) {
-        if (pref[i] > g_tile_pref) continue;
-        if (smem_layout(W, W + g_ring_extra, pref[i], V, wild).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+        if (pref[i] > tile_pref) continue;
+        if (smem_layout(W, W + ring_extra, pref[i], V, wild).total * static_cast<uint32_t>(want_ctas) <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     }
     for (int i = 0; i < 4 && chosen < 0; ++i)         // nothing reaches the occupancy target: the longest tile that fits at all
-        if (pref[i] <= g_tile_pref && smem_layout(W, 2, pref[i], V, wild).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
+        if (pref[i] <= tile_pref && smem_layout(W, 2, pref[i], V, wild).total <= static_cast<uint32_t>(SMEM_LIMIT)) chosen = pref[i];
     if (chosen < 0) return -1;
-    int nb = std::max(2, W + g_ring_extra);
+    int nb = std::max(2, W + ring_extra);
     while (nb > 2 && smem_layout(W, nb, chosen, V, wild).total > static_cast<uint32_t>(SMEM_LIMIT)) --nb;
     *TE = chosen; *NB = nb;
     *smem = smem_layout(W, nb, chosen, V, wild).total;
@@ -235,9 +244,9 @@ extern "C" int wxb_segment_warps(int32_t n_tokens) {
     return shape_of(n_tokens, &W, &K) ? W : -1;
 }
 extern "C" int wxb_set_k_target(int k_target) {
-    const int old = g_k_target;
-    if (k_target > 0) g_k_target = std::max(1, std::min(KMAX, k_target));
-    if (k_target < 0) g_k_target = 0;            // back to the per-batch choice
+    const int old = g_k_target.load();
+    if (k_target > 0) g_k_target.store(std::max(1, std::min(KMAX, k_target)));
+    if (k_target < 0) g_k_target.store(0);       // back to the per-batch choice
     return old;
 }
 
@@ -258,15 +267,17 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     if (const char *e = getenv("WXB_SIDE_STREAMS")) c->side_streams = std::max(1, std::min(NSIDE, atoi(e)));
     if (const char *e = getenv("WXB_TRACE")) c->want_trace = atoi(e) != 0;
     if (const char *e = getenv("WXB_GRAPHS")) c->use_graphs = atoi(e) != 0;
-    if (const char *e = getenv("WXB_K_TARGET")) g_k_target = std::max(1, std::min(KMAX, atoi(e)));
-    if (const char *e = getenv("WXB_TILE_FRAMES")) g_tile_pref = std::max(4, std::min(32, atoi(e)));
-    if (const char *e = getenv("WXB_RING_EXTRA")) g_ring_extra = std::max(1, std::min(4, atoi(e)));
+    if (const char *e = getenv("WXB_K_TARGET")) c->k_target = std::max(1, std::min(KMAX, atoi(e)));
+    if (const char *e = getenv("WXB_TILE_FRAMES")) c->tile_pref = std::max(4, std::min(32, atoi(e)));
+    if (const char *e = getenv("WXB_RING_EXTRA")) c->ring_extra = std::max(1, std::min(4, atoi(e)));
+    if (const char *e = getenv("WXB_CHUNK_TAPER")) c->chunk_taper = atoi(e) != 0;
     if (const char *e = getenv("WXB_CHUNK_MB")) c->chunk_bytes = static_cast<size_t>(std::max(1, atoi(e))) << 20;
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev_dbg[i]);
     for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -285,7 +296,7 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->wild, &c->nframes_scratch, &c->wide_lp, &c->h_emis, &c->h_path_tok};
+    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->wild, &c->nframes_scratch, &c->wide_lp, &c->spk_best, &c->h_emis, &c->h_path_tok};
     for (DevBuf *b : bufs) b->release();
     for (auto &b : c->h_i32) b.release();
     for (auto &b : c->h_f64) b.release();
@@ -297,6 +308,7 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     if (c->copy) cudaStreamDestroy(c->copy);
     if (c->d2h) cudaStreamDestroy(c->d2h);
     if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
+    if (c->ev_busy) cudaEventDestroy(c->ev_busy);
     for (int i = 0; i < 3; ++i) if (c->ev_dbg[i]) cudaEventDestroy(c->ev_dbg[i]);
     for (int i = 0; i < NSIDE; ++i) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
@@ -336,10 +348,29 @@ static void plan_free(wxb_plan *pl) {
     delete pl;
 }
 
-// chunk_rows = 0: one chunk (the emissions are already resident).  Otherwise the emission matrix
-// arrives in chunks of chunk_rows rows (wxb_align_host starts those copies before planning) and a
-// segment belongs to the chunk that holds its last row: its kernels wait for that chunk only.
-static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_rows, wxb_plan **out, bool copy_engine_busy = false) {
+// Row boundaries of the host->device emission chunks of wxb_align_host: full chunks of chunk_rows rows, then a
+// tapered tail (1/2, 1/4, 1/8 of a chunk).  What is left to do when the last byte has landed is the kernels and
+// result copies of the last chunk's segments only, so the smaller that chunk, the closer the call ends to the
+// link's own time (64 MB last chunk: ~0.45 ms of tail on the 4,096-segment benchmark batch; 8 MB: ~0.1 ms).
+static std::vector<int64_t> make_chunk_bounds(int64_t rows, int64_t chunk_rows, bool taper) {
+    std::vector<int64_t> b{0};
+    if (rows <= 0) { b.push_back(0); return b; }
+    int64_t tail[3] = {chunk_rows / 2, chunk_rows / 4, chunk_rows / 8};
+    const bool use_tail = taper && chunk_rows >= 8 && rows > 2 * chunk_rows;
+    const int64_t tail_total = use_tail ? tail[0] + tail[1] + tail[2] : 0;
+    int64_t r = 0;
+    while (rows - tail_total - r > chunk_rows) { r += chunk_rows; b.push_back(r); }
+    if (!use_tail) { b.push_back(rows); return b; }
+    r = rows - tail_total;
+    b.push_back(r);
+    for (int i = 0; i < 3; ++i) { r += tail[i]; b.push_back(r); }
+    return b;
+}
+
+// bounds = nullptr: one chunk (the emissions are already resident).  Otherwise the emission matrix arrives in
+// chunks with the given row boundaries (wxb_align_host starts those copies before planning) and a segment
+// belongs to the chunk that holds its last row: its kernels wait for that chunk only.
+static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, const std::vector<int64_t> *bounds, wxb_plan **out, bool copy_engine_busy = false) {
     if (!ctx || !bt || !out) return fail(WXB_EINVAL, "wxb_plan_create: NULL argument");
     *out = nullptr;
     const int64_t S = bt->n_segments;
@@ -396,11 +427,10 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     long long trellis_off = 0;
     int wmax = 1;
     const bool no_shortcut = (bt->flags & WXB_F_NO_SHORTCUT) != 0;
-    const int k_target = g_k_target > 0 ? g_k_target : pick_k_target(to, fo, bt->frame_len, S, ctx->sm_count, pl->V);
-    pl->chunk_row.push_back(0);
-    if (chunk_rows > 0)
-        for (int64_t r = chunk_rows; r < fo[S]; r += chunk_rows) pl->chunk_row.push_back(r);
-    pl->chunk_row.push_back(fo[S]);
+    const int k_forced = ctx->k_target > 0 ? ctx->k_target : g_k_target.load(std::memory_order_relaxed);
+    const int k_target = k_forced > 0 ? k_forced : pick_k_target(to, fo, bt->frame_len, S, ctx->sm_count, pl->V);
+    if (bounds && bounds->size() >= 2 && bounds->front() == 0 && bounds->back() == fo[S]) pl->chunk_row = *bounds;
+    else { pl->chunk_row.push_back(0); pl->chunk_row.push_back(fo[S]); }
     const int n_chunks = static_cast<int>(pl->chunk_row.size()) - 1;
     pl->chunk_seg.assign(static_cast<size_t>(n_chunks) + 1, S);
     pl->chunk_seg[0] = 0;
@@ -408,8 +438,11 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     for (int64_t s = 0; s < S; ++s) {
         const int T = bt->frame_len ? bt->frame_len[s] : static_cast<int>(fo[s + 1] - fo[s]);
         const int N = static_cast<int>(to[s + 1] - to[s]);
-        const int chunk = chunk_rows > 0 ? static_cast<int>(std::min<int64_t>((fo[s] + std::max(T, 1) - 1) / chunk_rows, n_chunks - 1)) : 0;
-        for (; chunk_prev < chunk; ++chunk_prev) pl->chunk_seg[chunk_prev + 1] = s;     // last rows are non-decreasing in s
+        // chunk holding the segment's last row; last rows are non-decreasing in s, so the search only moves forward
+        int chunk = chunk_prev;
+        const int64_t last_row = fo[s] + std::max(T, 1) - 1;
+        while (chunk + 1 < n_chunks && last_row >= pl->chunk_row[chunk + 1]) ++chunk;
+        for (; chunk_prev < chunk; ++chunk_prev) pl->chunk_seg[chunk_prev + 1] = s;
         const long long this_trellis = trellis_off;
         trellis_off += static_cast<long long>(T + 1) * (N + 1);
         int K = -1, Wc = 0;
@@ -436,7 +469,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
     pl->n_short = static_cast<int>(shorts.size());
     {
         int te, nbq; size_t sm;
-        if (pick_shape(wmax, pl->V, pl->has_wild, &te, &nbq, &sm) != 0)
+        if (pick_shape(ctx->tile_pref, ctx->ring_extra, wmax, pl->V, pl->has_wild, &te, &nbq, &sm) != 0)
             return fail(WXB_EUNSUPPORTED, "wxb_plan_create: vocab %d needs more than %d bytes of shared memory for a %d-warp segment", pl->V, SMEM_LIMIT, wmax);
     }
     // one launch per (chunk, warps, tokens-per-lane) class; longest-first inside a class: the block
@@ -454,7 +487,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
         bits += static_cast<long long>((descs[i].T + 31) / 32) * descs[i].W * descs[i].K * 32;
         if (i == 0 || descs[i].K != descs[i - 1].K || descs[i].W != descs[i - 1].W || descs[i].pad != descs[i - 1].pad) {
             Bucket b{descs[i].K, descs[i].W, 0, 0, 0, static_cast<int>(i), 0, 0, descs[i].T, descs[i].pad, fin_next, 0};
-            pick_shape(b.W, pl->V, pl->has_wild, &b.TE, &b.NB, &b.smem);
+            pick_shape(ctx->tile_pref, ctx->ring_extra, b.W, pl->V, pl->has_wild, &b.TE, &b.NB, &b.smem);
             pl->buckets.push_back(b);
         }
         pl->buckets.back().count += 1;
@@ -570,7 +603,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, int64_t chunk_row
 }
 
 extern "C" int wxb_plan_create(wxb_ctx *ctx, const wxb_batch *bt, wxb_plan **out) {
-    return plan_create_impl(ctx, bt, 0, out);
+    return plan_create_impl(ctx, bt, nullptr, out);
 }
 
 extern "C" void wxb_plan_destroy(wxb_plan *plan) {
@@ -864,9 +897,32 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
 // A plan that is run again and again on the same buffers (steady-state serving, bench.py) is a fixed
 // DAG of ~25 launches over 8 side streams joined by events: from the third identical call on it is
 // replayed as one CUDA graph, which removes the per-step event/launch latencies between steps.
+static int plan_run_unserialised(wxb_plan *pl, const float *emis, const wxb_outputs *o, cudaStream_t st, float *elapsed_dp_ms);
+
+// All plans of a ctx share its scratch (choice bits, p0, ...) and side streams: two runs in flight on different
+// caller streams would race on them.  Every run therefore waits for the previous run of the same ctx (an event
+// recorded at its end) before it starts — a no-op when the caller uses one stream, which is the fast case.
 extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *o, void *stream_, float *elapsed_dp_ms) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
+    wxb_ctx *c = pl->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+    const bool serialise = cap == cudaStreamCaptureStatusNone && pl->S > 0;
+    if (serialise && c->last_run_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_busy, 0));
+    const int rc = plan_run_unserialised(pl, emis, o, st, elapsed_dp_ms);
+    if (serialise && rc == WXB_OK) {
+        CUDA_TRY(cudaEventRecord(c->ev_busy, st));
+        c->last_run_stream = st;
+    }
+    return rc;
+}
+
+// A plan that is run again and again on the same buffers (steady-state serving, bench.py) is a fixed
+// DAG of ~25 launches over 8 side streams joined by events: from the third identical call on it is
+// replayed as one CUDA graph, which removes the per-step event/launch latencies between steps.
+static int plan_run_unserialised(wxb_plan *pl, const float *emis, const wxb_outputs *o, cudaStream_t st, float *elapsed_dp_ms) {
     wxb_ctx *c = pl->ctx;
     if (elapsed_dp_ms || !c->use_graphs || c->want_trace || pl->graph_off || pl->S == 0 || (pl->flags & WXB_F_CLOBBER))
         return run_impl(pl, emis, nullptr, o, st, elapsed_dp_ms);
@@ -938,10 +994,12 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
         chunk_rows = std::max<int64_t>(1, static_cast<int64_t>(c->chunk_bytes / (4ull * bt->vocab)));
     }
     int n_chunks = 0;
+    std::vector<int64_t> bounds;
     if (rows > 0) {
         const size_t V = static_cast<size_t>(bt->vocab);
         CUDA_TRY(c->h_emis.ensure(static_cast<size_t>(rows) * V * 4));
-        n_chunks = static_cast<int>((rows + chunk_rows - 1) / chunk_rows);
+        bounds = make_chunk_bounds(rows, chunk_rows, c->chunk_taper);
+        n_chunks = static_cast<int>(bounds.size()) - 1;
         while (static_cast<int>(c->ev_chunk.size()) < n_chunks) {
             cudaEvent_t ev;
             CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -949,9 +1007,10 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
         }
         if (timing) CUDA_TRY(cudaEventRecord(c->ev_t0, c->copy));
         for (int k = 0; k < n_chunks; ++k) {
-            const int64_t r0 = k * chunk_rows, r1 = std::min(rows, r0 + chunk_rows);
-            CUDA_TRY(cudaMemcpyAsync(c->h_emis.as<float>() + r0 * V, emis_host + r0 * V, static_cast<size_t>(r1 - r0) * V * 4,
-                                     cudaMemcpyHostToDevice, c->copy));
+            const int64_t r0 = bounds[k], r1 = bounds[k + 1];
+            if (r1 > r0)
+                CUDA_TRY(cudaMemcpyAsync(c->h_emis.as<float>() + r0 * V, emis_host + r0 * V, static_cast<size_t>(r1 - r0) * V * 4,
+                                         cudaMemcpyHostToDevice, c->copy));
             CUDA_TRY(cudaEventRecord(c->ev_chunk[k], c->copy));
         }
         if (timing) CUDA_TRY(cudaEventRecord(c->ev_t1, c->copy));
@@ -959,7 +1018,7 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
     // 2. plan while the copy engine works
     const double t_copies = now();
     wxb_plan *pl = nullptr;
-    int rc = plan_create_impl(c, bt, chunk_rows, &pl, /*copy_engine_busy=*/n_chunks > 0);
+    int rc = plan_create_impl(c, bt, n_chunks > 0 ? &bounds : nullptr, &pl, /*copy_engine_busy=*/n_chunks > 0);
     const double t_plan = now();
     if (rc != WXB_OK) { cudaStreamSynchronize(c->copy); return rc; }
     struct Guard { wxb_plan *p; wxb_ctx *c; ~Guard() { cudaStreamSynchronize(c->copy); wxb_plan_destroy(p); } } guard{pl, c};
@@ -1064,15 +1123,25 @@ extern "C" int wxb_assign_speakers_device(wxb_ctx *ctx, const double *diar_start
                                           int32_t fill_nearest, int32_t *out_speaker, void *stream) {
     if (!ctx) return fail(WXB_EINVAL, "wxb_assign_speakers: ctx is NULL");
     if (n_diar < 0 || n_query < 0) return fail(WXB_EINVAL, "wxb_assign_speakers: negative count");
-    if (n_speakers < 0 || n_speakers > SPK_MAX) return fail(WXB_EUNSUPPORTED, "wxb_assign_speakers: %d speakers; at most %d are supported", n_speakers, SPK_MAX);
+    if (n_speakers < 0) return fail(WXB_EINVAL, "wxb_assign_speakers: n_speakers < 0");
     if (n_query == 0) return WXB_OK;
     if (!query_start || !query_end || !out_speaker || (n_diar > 0 && (!diar_start || !diar_end || !diar_speaker)))
         return fail(WXB_EINVAL, "wxb_assign_speakers: NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long blocks = (n_query + 127) / 128;
-    assign_speakers_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        diar_start, diar_end, diar_speaker, n_diar, n_speakers, query_start, query_end, n_query, fill_nearest, out_speaker);
-    CUDA_TRY(cudaGetLastError());
+    // up to SPK_MAX speakers fit one launch; more go through successive launches that carry the running winner
+    double *best_sum = nullptr;
+    if (n_speakers > SPK_MAX) {
+        CUDA_TRY(ctx->spk_best.ensure(static_cast<size_t>(n_query) * 8));
+        best_sum = ctx->spk_best.as<double>();
+    }
+    for (int base = 0; base == 0 || base < n_speakers; base += SPK_MAX) {
+        assign_speakers_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
+            diar_start, diar_end, diar_speaker, n_diar, base, std::min(SPK_MAX, std::max(n_speakers - base, 0)), query_start, query_end,
+            n_query, fill_nearest, out_speaker, best_sum);
+        CUDA_TRY(cudaGetLastError());
+    }
     return WXB_OK;
 }
 
@@ -1105,6 +1174,49 @@ extern "C" int wxb_assign_speakers_host(wxb_ctx *ctx, const double *diar_start, 
     if (rc != WXB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_speaker, ctx->h_i32[1].p, nq * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return WXB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: exact scores on the host
+extern "C" int wxb_exact_scores_host(const wxb_batch *bt, const float *path_prob, const int32_t *status,
+                                     const int32_t *char_start, const int32_t *char_end,
+                                     double *char_score, double *char_score_r, double *word_score) {
+    if (!bt || !status || !char_start || !char_end || !char_score) return fail(WXB_EINVAL, "wxb_exact_scores_host: NULL argument");
+    const int64_t S = bt->n_segments;
+    if (S <= 0) return WXB_OK;
+    if (!bt->frame_off || !bt->tok_off) return fail(WXB_EINVAL, "wxb_exact_scores_host: frame_off/tok_off is NULL");
+    if (!path_prob && bt->frame_off[S] > 0) return fail(WXB_EINVAL, "wxb_exact_scores_host: path_prob is NULL");
+    const double nan = std::nan("");
+    for (int64_t s = 0; s < S; ++s) {
+        const int64_t k0 = bt->tok_off[s], k1 = bt->tok_off[s + 1];
+        const int64_t T = bt->frame_len ? bt->frame_len[s] : bt->frame_off[s + 1] - bt->frame_off[s];
+        const float *p = path_prob + bt->frame_off[s];
+        for (int64_t k = k0; k < k1; ++k) {
+            if (status[s] != WXB_SEG_OK) { char_score[k] = nan; if (char_score_r) char_score_r[k] = nan; continue; }
+            const int a = char_start[k], b = char_end[k];
+            if (a < 0 || b <= a || b > T) return fail(WXB_EINVAL, "wxb_exact_scores_host: char %lld of segment %lld spans [%d,%d) outside its %lld frames", (long long)(k - k0), (long long)s, a, b, (long long)T);
+            double sum = static_cast<double>(p[a]);                   // Python sum(): 0 + p_first + ...
+            for (int f = a + 1; f < b; ++f) sum += static_cast<double>(p[f]);
+            const double score = sum / static_cast<double>(b - a);
+            char_score[k] = score;
+            if (char_score_r) char_score_r[k] = wxb::round3(score);
+        }
+    }
+    if (!word_score || bt->n_words <= 0) return WXB_OK;
+    if (!char_score_r || !bt->word_off || !bt->wchar_off || !bt->wchar_idx) return fail(WXB_EINVAL, "wxb_exact_scores_host: word scores need char_score_r and the word groups");
+    for (int64_t s = 0; s < S; ++s) {
+        const int64_t base = bt->tok_off[s];
+        for (int64_t w = bt->word_off[s]; w < bt->word_off[s + 1]; ++w) {
+            const int64_t lo = bt->wchar_off[w];
+            const long n = static_cast<long>(bt->wchar_off[w + 1] - lo);
+            long count = 0;
+            if (status[s] == WXB_SEG_OK)
+                for (long i = 0; i < n; ++i) count += bt->wchar_idx[lo + i] >= 0;
+            if (count == 0) { word_score[w] = nan; continue; }
+            const double sum = wxb::pairwise_sum([&](long i) { const int idx = bt->wchar_idx[lo + i]; return idx >= 0 ? char_score_r[base + idx] : 0.0; }, n);
+            word_score[w] = wxb::round3_np(sum / static_cast<double>(count));
+        }
+    }
     return WXB_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 namespace wxb {
 
@@ -12,20 +13,27 @@ static cudaError_t configure(size_t smem) {
     // Every instantiation asks for the maximum shared-memory carveout: kernels that want different
     // L1/shared splits cannot be co-resident on an SM, and a plan runs one launch per
     // (warps, tokens-per-lane) class concurrently.
-    static size_t configured_for = 0;
-    static bool first = true;
-    if (!first && smem <= configured_for) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(align_kernel<K, DEBUG, WILD>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared);
+    // Function attributes are per *device*: the cache is keyed on the current device (one engine per GPU may
+    // live in the same process) and guarded, since contexts may launch from different threads.
+    constexpr int MAX_DEV = 64;
+    static std::mutex mu;
+    static size_t configured_for[MAX_DEV] = {};      // 0 = this device has not been configured yet
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    const bool cached = dev >= 0 && dev < MAX_DEV;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached && configured_for[dev] != 0 && smem <= configured_for[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(align_kernel<K, DEBUG, WILD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    size_t now = 48 * 1024;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(align_kernel<K, DEBUG, WILD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        configured_for = 227 * 1024;
-    } else {
-        configured_for = std::max<size_t>(configured_for, 48 * 1024);
+        now = 227 * 1024;
     }
-    first = false;
+    if (cached) configured_for[dev] = std::max(configured_for[dev], now);
     return cudaSuccess;
 }
 

@@ -389,10 +389,14 @@ __global__ void __launch_bounds__(256) backtrack_trellis_kernel(const float *R, 
 // pandas' groupby-sum does (Kahan compensation, row order).
 constexpr int SPK_MAX = 64;
 constexpr int SPK_TILE = 256;
+// One launch handles speakers [spk_base, spk_base + n_spk), n_spk <= SPK_MAX.  More speakers than that are
+// covered by successive launches in ascending id order that carry the best (sum, id) so far in
+// best_sum / out: a later speaker replaces it only when strictly larger, which keeps the reference's
+// "ties to the first label".  Ids outside the launch's range are ignored (also protects the local arrays).
 __global__ void __launch_bounds__(128) assign_speakers_kernel(const double *d_start, const double *d_end, const int *d_spk,
-                                                              long long n_diar, int n_spk, const double *q_start,
+                                                              long long n_diar, int spk_base, int n_spk, const double *q_start,
                                                               const double *q_end, long long n_query, int fill_nearest,
-                                                              int *out) {
+                                                              int *out, double *best_sum) {
     __shared__ double s_start[SPK_TILE], s_end[SPK_TILE];
     __shared__ int s_spk[SPK_TILE];
     const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -411,8 +415,8 @@ __global__ void __launch_bounds__(128) assign_speakers_kernel(const double *d_st
         if (!live) continue;
         for (int i = 0; i < n; ++i) {
             const double inter = fmin(s_end[i], qe) - fmax(s_start[i], qs);
-            if (fill_nearest || inter > 0.0) {
-                const int k = s_spk[i];
+            const int k = s_spk[i] - spk_base;
+            if ((fill_nearest || inter > 0.0) && k >= 0 && k < n_spk) {
                 const double y = inter - comp[k];
                 const double t = sum[k] + y;
                 comp[k] = (t - sum[k]) - y;
@@ -426,7 +430,10 @@ __global__ void __launch_bounds__(128) assign_speakers_kernel(const double *d_st
     for (int k = 0; k < n_spk; ++k)
         if ((seen >> k) & 1ull)
             if (best < 0 || sum[k] > sum[best]) best = k;      // descending sort, ties keep label order
-    out[q] = best;
+    if (!best_sum) { out[q] = best < 0 ? -1 : spk_base + best; return; }
+    const int prev = spk_base > 0 ? out[q] : -1;                // earlier launches' winner
+    if (best >= 0 && (prev < 0 || sum[best] > best_sum[q])) { out[q] = spk_base + best; best_sum[q] = sum[best]; }
+    else if (spk_base == 0) out[q] = -1;
 }
 
 }  // namespace wxb

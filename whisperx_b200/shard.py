@@ -62,9 +62,11 @@ def align_sharded(transcript, model, align_model_metadata, audio, device, interp
         raise RuntimeError("aligner returned a different number of segment groups than it was given")
     payload = list(zip(mine, grouped))
     if distributed and world > 1:
-        gathered = [None] * world if rank == dst else None
+        # `dst` is a global rank (that is what gather_object takes); `rank` above is group-local
+        is_dst = dist.get_rank() == dst
+        gathered = [None] * world if is_dst else None
         dist.gather_object(payload, gathered, dst=dst, group=group)
-        if rank != dst:
+        if not is_dst:
             return None
         payload = [item for part in gathered for item in part]
     payload.sort(key=lambda item: item[0])

@@ -118,3 +118,82 @@ def make_batch(n_segments: int, config: str = "c2", seed0: int = 1234, vocab: Op
         tok_off.append(tok_off[-1] + N)
     return SynthBatch(np.concatenate(em, 0), np.asarray(frame_off, np.int64), np.asarray(lens, np.int32),
                       np.asarray(tok_off, np.int64), np.concatenate(toks), np.asarray(durs), V, blank)
+
+
+# ----------------------------------------------------------------------------- on-device sweep generator
+# BASELINE configs[4] (10,000 audio-hours = 1.2 M x 30 s segments) is 208 GB of float32 emissions: it cannot
+# be staged from the host, so the sweep's batches are generated on the GPU, one batch at a time, by a
+# counter-based generator: every value is a pure function of (segment id, element index), so any rank of
+# any world size produces bit-identical data for the segments it owns.  Same distributions as make_batch
+# (D1 iid N(0,9); D2 planted), different random streams.
+_M64 = (1 << 64) - 1
+
+
+def _i64(c: int) -> int:
+    """Python int -> the int64 with the same 64 bits (torch integer arithmetic wraps)."""
+    c &= _M64
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _mix64(x):
+    """splitmix64 finaliser on an int64 tensor (logical shifts emulated by masking the arithmetic ones)."""
+    x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * _i64(0xBF58476D1CE4E5B9)
+    x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * _i64(0x94D049BB133111EB)
+    return x ^ ((x >> 31) & ((1 << 33) - 1))
+
+
+def _uniform24(h, shift: int):
+    """24 bits of the hash -> float32 in (0, 1)."""
+    import torch
+    return (((h >> shift) & 0xFFFFFF).to(torch.float32) + 0.5) * (1.0 / 16777216.0)
+
+
+def device_sweep_batch(seg_ids, device, duration_s: float = 30.0, vocab: int = 29, blank: int = 0, sep: int = 1,
+                       kind: str = "iid", seed: int = 1234):
+    """One batch of the sweep for the given segment ids (all `duration_s` long, N = round(13.3 * d) tokens).
+
+    Returns (emissions [S * Tp, V] float32 CUDA tensor of raw logits, SynthBatch-like host metadata with
+    `emissions=None`).  Tp = T rounded up to 4 rows (16-byte aligned segment starts); pad rows are zero.
+    Tokens: separator with probability 2/11 (never first/last or doubled), else a uniform non-blank,
+    non-separator symbol — generated on the device from the same hash and copied to the host (the C ABI takes
+    token ids from host memory)."""
+    import torch
+    dev = torch.device(device)
+    ids = torch.as_tensor(np.asarray(seg_ids, dtype=np.int64), device=dev)
+    S = int(ids.numel())
+    T = frames_for(duration_s)
+    Tp = T + (-T) % 4
+    N = max(int(round(CHARS_PER_SECOND * duration_s)), 1)
+    key = _mix64(ids * _i64(0x9E3779B97F4A7C15) + _i64(seed))                      # [S] per-segment key
+    # tokens
+    k = torch.arange(N, device=dev, dtype=torch.int64)
+    ht = _mix64(key[:, None] + (k[None, :] + 1) * _i64(0xD1B54A32D192ED03))
+    letters = torch.tensor([v for v in range(vocab) if v != blank and v != sep], device=dev, dtype=torch.int64)
+    tok = letters[((ht >> 8) & 0x7FFFFFFF) % letters.numel()]
+    is_sep = ((ht >> 44) & 0xFFFF) < (0x10000 * 2 // 11)
+    is_sep[:, 0] = False
+    is_sep[:, -1] = False
+    is_sep[:, 1:] &= ~is_sep[:, :-1]
+    tok = torch.where(is_sep, torch.full_like(tok, sep), tok)
+    # logits, in row blocks to bound the int64 temporaries
+    em = torch.zeros((S, Tp, vocab), dtype=torch.float32, device=dev)
+    e_idx = torch.arange(T * vocab, device=dev, dtype=torch.int64)
+    step = max(1, (1 << 27) // (T * vocab))
+    for a in range(0, S, step):
+        h = _mix64(key[a:a + step, None] ^ ((e_idx[None, :] + 1) * _i64(0xA0761D6478BD642F)))
+        z = torch.sqrt(-2.0 * torch.log(_uniform24(h, 40))) * torch.cos(6.283185307179586 * _uniform24(h, 12))
+        em[a:a + step, :T] = (z * 3.0).view(-1, T, vocab)
+    if kind == "planted":
+        f = torch.arange(T, device=dev, dtype=torch.int64)
+        hk = _mix64(key[:, None] + (f[None, :] + 1) * _i64(0xE7037ED1A0B428DB)) & ((1 << 62) - 1)
+        thresh = torch.sort(hk, dim=1).values[:, N - 1:N]               # the N frames with the smallest keys enter a token
+        entry = hk <= thresh
+        which = torch.cumsum(entry, 1) - 1
+        col = torch.where(entry, torch.gather(tok, 1, which.clamp(0, N - 1)), torch.full_like(which, blank))
+        em[:, :T].scatter_add_(2, col[:, :, None], torch.full((S, T, 1), 8.0, device=dev))
+    elif kind != "iid":
+        raise ValueError(kind)
+    meta = SynthBatch(None, np.arange(S + 1, dtype=np.int64) * Tp, np.full(S, T, np.int32),
+                      np.arange(S + 1, dtype=np.int64) * N, tok.to(torch.int32).cpu().numpy().reshape(-1),
+                      np.full(S, float(duration_s)), vocab, blank)
+    return em.view(S * Tp, vocab), meta
