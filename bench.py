@@ -287,22 +287,26 @@ def _spec_of(meta, logits=True):
 
 
 def time_device_batch(eng, dev, meta, em_dev, steps, warmup, peak, n_parity, logits=True):
-    """K device-timed passes over one resident batch + an in-run parity sample of that batch."""
+    """K device-timed passes over one resident batch (the overlapped serving loop of `value`: two steps in
+    flight) + an in-run parity sample of that batch."""
     import torch
     from whisperx_b200.engine import _alloc_outputs
     spec = _spec_of(meta, logits)
     plan = eng.plan(spec)
-    out = _alloc_outputs(spec, dev, ())
-    for _ in range(warmup):
-        plan.run(em_dev, out=out)
+    outs = [_alloc_outputs(spec, dev, ()) for _ in range(2)]
+    for i in range(warmup):
+        plan.run_overlapped(em_dev, outs[i % 2])
+    eng.join()
     torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(steps):
-        plan.run(em_dev, out=out)
+    for i in range(steps):
+        plan.run_overlapped(em_dev, outs[i % 2])
+    eng.join()
     ev1.record()
     torch.cuda.synchronize(dev)
     ms = ev0.elapsed_time(ev1) / steps
+    out = outs[(steps - 1) % 2]
     checked = parity_sample(eng, em_dev, meta, out, n_parity, logits) if n_parity else 0
     rec = {"segments": len(meta.frame_len), "audio_hours": meta.audio_seconds / 3600.0, "cells": int(plan.cells),
            "steps": steps, "ms_per_step": ms, "value": meta.audio_seconds / 3600.0 / (ms * 1e-3), "unit": UNIT,
@@ -399,13 +403,15 @@ def align_api_configs(dev, steps):
     return recs
 
 
-def strong_sweep(eng, dev, rank, world, hours, kind, barrier, peak):
+def strong_sweep(eng, dev, rank, world, hours, kind, barrier, peak, group=16):
     """BASELINE configs[4]: a fixed pool of 30 s segments (10,000 audio-hours = 1.2 M segments by default),
     partitioned over the ranks with whisperx_b200.shard.partition_lpt; every rank generates its segments on its
     GPU (counter-based generator: the data of a segment does not depend on the rank or world size), aligns them
-    batch by batch and keeps an order-independent checksum of every character's frames.  Timed: CUDA events
-    around each batch's wxb_plan_run (emissions resident when it starts); the generator is the data source and is
-    outside.  Returns this rank's figures; the caller reduces them over ranks."""
+    batch by batch and keeps an order-independent checksum of every character's frames.
+    The rank's batches go through in groups of `group`: the group's emissions are generated and its plans made
+    (the data source and the host-side planning: untimed, as for `value`), then the group is aligned back to back
+    through the overlapped serving loop between two CUDA events (emissions resident when the clock starts).
+    Timed = the sum over groups.  Returns this rank's figures; the caller reduces them over ranks."""
     import torch
     from whisperx_b200 import shard, synth
     from whisperx_b200.engine import _alloc_outputs
@@ -424,38 +430,41 @@ def strong_sweep(eng, dev, rank, world, hours, kind, barrier, peak):
     evs = []
     checksum = torch.zeros((), dtype=torch.int64, device=dev)
     failed = torch.zeros((), dtype=torch.int64, device=dev)
-    prev_plan = None
-    launches = 0
-    checked = 0
-    cells = 0
-    out = None
+    launches = checked = cells = 0
+    outs = []
     barrier()
     w0 = time.perf_counter()
-    for b, ids in enumerate(chunks):
-        em, meta = synth.device_sweep_batch(ids, dev, kind=kind)
-        spec = _spec_of(meta, True)
-        plan = eng.plan(spec)
-        if out is None or out.char_start.numel() < spec.sum_N or out.status.numel() != spec.n_segments:
-            out = _alloc_outputs(spec, dev, ())
+    for g0 in range(0, len(chunks), group):
+        work = []
+        for ids in chunks[g0:g0 + group]:
+            em, meta = synth.device_sweep_batch(ids, dev, kind=kind)
+            spec = _spec_of(meta, True)
+            work.append((em, meta, spec, eng.plan(spec)))
+        while len(outs) < len(work):
+            outs.append(_alloc_outputs(work[0][2], dev, ()))
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        plan.run(em, out=out)
+        for i, (em, meta, spec, plan) in enumerate(work):
+            plan.run_overlapped(em, outs[i])
+        eng.join()
         e1.record()
         evs.append((e0, e1))
-        checksum += out.char_start[:spec.sum_N].sum(dtype=torch.int64) * 3 + out.char_end[:spec.sum_N].sum(dtype=torch.int64)
-        failed += out.status[:spec.n_segments].sum(dtype=torch.int64)
-        launches += plan.launches
-        cells += plan.cells
-        if b in (0, len(chunks) - 1):
-            torch.cuda.synchronize(dev)
-            checked += parity_sample(eng, em, meta, out, 4, True, seed=b)
-        if prev_plan is not None:
-            prev_plan.close()
-        prev_plan = plan
+        for i, (em, meta, spec, plan) in enumerate(work):
+            o = outs[i]
+            checksum += o.char_start[:spec.sum_N].sum(dtype=torch.int64) * 3 + o.char_end[:spec.sum_N].sum(dtype=torch.int64)
+            failed += o.status[:spec.n_segments].sum(dtype=torch.int64)
+            launches += plan.launches
+            cells += plan.cells
+        torch.cuda.synchronize(dev)
+        if g0 == 0 or g0 + group >= len(chunks):
+            em, meta, spec, plan = work[-1]
+            checked += parity_sample(eng, em, meta, outs[len(work) - 1], 4, True, seed=g0)
+        for _, _, _, plan in work:
+            plan.close()
+        del work
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - w0
-    if prev_plan is not None:
-        prev_plan.close()
     align_ms = sum(a.elapsed_time(b) for a, b in evs)
     return {"align_ms": align_ms, "wall_s": wall, "segments": len(mine), "batches": len(chunks), "cells": cells,
             "checksum": int(checksum.item()), "failed": int(failed.item()), "launches": launches, "parity_checked": checked,
@@ -519,18 +528,35 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- resident-in-HBM timing (value) ----
-    for _ in range(args.warmup):
-        plan.run(dev_em, out=out)
+    # A serving loop: step after step over resident batches through wxb_plan_run_async — up to two steps in flight
+    # (two scratch sets, two groups of side streams), so the tail of a step, when its last long segments leave most
+    # SMs idle, is filled by the head of the next.  Every step is a complete pass; K steps are bracketed by CUDA
+    # events and a join.  `value_serial` is the same loop with one step in flight at a time (wxb_plan_run).
+    out2 = _alloc_outputs(spec, dev, ())
+    for i in range(args.warmup):
+        plan.run_overlapped(dev_em, out if i % 2 == 0 else out2)
+    eng.join()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    for i in range(args.steps):
+        plan.run_overlapped(dev_em, out if i % 2 == 0 else out2)
+    eng.join()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    for _ in range(args.warmup):
+        plan.run(dev_em, out=out)
+    barrier()
+    ev0.record()
     for _ in range(args.steps):
         plan.run(dev_em, out=out)
     ev1.record()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_serial = ev0.elapsed_time(ev1) / args.steps
+    assert torch.equal(out.char_start, out2.char_start) and torch.equal(out.char_score, out2.char_score)
     # dominant kernel alone (all align_kernel launches of one step run concurrently on side streams;
     # the library brackets them with CUDA events on the launching stream)
     dp_ms = []
@@ -606,7 +632,7 @@ def run_ours(args):
         strong = strong_sweep(eng, dev, rank, world, args.sweep_hours, args.sweep_kind, barrier, peak)
 
     t = torch.tensor([ms_total, e2e_s * 1e3, floor[0], floor[1], planted["ms_per_step"] if planted else 0.0,
-                      strong["align_ms"] if strong else 0.0, strong["wall_s"] if strong else 0.0], device=dev, dtype=torch.float64)
+                      strong["align_ms"] if strong else 0.0, strong["wall_s"] if strong else 0.0, ms_serial], device=dev, dtype=torch.float64)
     units = torch.tensor([batch.audio_seconds, float(plan.cells), float(planted["parity_checked"]) if planted else 0.0,
                           float(strong["cells"]) if strong else 0.0, float(strong["segments"]) if strong else 0.0,
                           float(strong["parity_checked"]) if strong else 0.0, float(strong["failed"]) if strong else 0.0,
@@ -616,7 +642,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
         dist.all_reduce(csum, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, floor_h2d, floor_d2h, planted_ms, strong_ms, strong_wall = (float(x) for x in t)
+    ms_total, e2e_ms, floor_h2d, floor_d2h, planted_ms, strong_ms, strong_wall, ms_serial_max = (float(x) for x in t)
     audio_all, cells_all = float(units[0]), float(units[1])
 
     if rank == 0:
@@ -632,6 +658,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "cells_per_s": cells_all / (ms_step * 1e-3),
+            "value_serial": {"value": audio_all / 3600.0 / (ms_serial_max * 1e-3), "ms_per_step": ms_serial_max,
+                             "note": "one step in flight at a time (wxb_plan_run, CUDA-graph replay); `value` keeps two in flight (wxb_plan_run_async)"},
             "parity_checked": int(units[8]),
             "config": {"workload": WORKLOAD_TEXT[args.workload].format(n=nseg),
                        "segments_per_gpu": nseg, "workload_id": args.workload, "audio_hours_per_gpu": batch.audio_seconds / 3600.0,
@@ -685,7 +713,8 @@ def run_ours(args):
                 "lpt_imbalance": strong["lpt_imbalance"], "failed_segments": int(units[6]), "gpu_launches": int(units[7]),
                 "checksum": int(csum[0]), "checksum_note": "sum over all characters of 3*start_frame + end_frame, summed over ranks: equal at every N",
                 "parity_checked": int(units[5]),
-                "timed": "sum over the rank's batches of the CUDA-event time around wxb_plan_run (emissions resident); max over ranks",
+                "timed": "the rank's batches go through in groups of 16: per group, emissions generated and plans made (untimed), then the group "
+                         "aligned back to back (wxb_plan_run_async, two batches in flight) between two CUDA events; sum over groups, max over ranks",
             }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

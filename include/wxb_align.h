@@ -141,10 +141,19 @@ int  wxb_plan_stats(const wxb_plan *plan, int64_t *cells, int64_t *alg_bytes, in
  * the DP kernels alone.  Calls that repeat the same (emissions, outputs) pointers are replayed as a
  * CUDA graph from the third one on (WXB_GRAPHS=0 disables).
  * All plans of a ctx share its scratch buffers and side streams: a run waits (on the device, through an event)
- * for the previous run of the same ctx, whatever stream that was enqueued on, so runs of one ctx never overlap.
+ * for the previous wxb_plan_run of the same ctx, whatever stream that was enqueued on.
  * Calls into one ctx must come from one host thread at a time; use one ctx per thread / per GPU for concurrency. */
 int  wxb_plan_run(wxb_plan *plan, const float *emissions_dev, const wxb_outputs *out_dev,
                   void *stream, float *elapsed_dp_ms);
+
+/* Overlapped runs (a serving loop over many batches): same work as wxb_plan_run, but `stream` is not made to wait
+ * for it.  Calls alternate between the ctx's two run slots (each has its own scratch and side streams), so up to
+ * two runs are in flight and the tail of one batch — its last, longest segments, when most SMs have run out of
+ * work — is filled by the head of the next; call n+2 waits on the device for call n.  wxb_ctx_join makes `stream`
+ * wait for every outstanding run of the ctx: results are complete once `stream` has passed that point.  The
+ * caller must not hand an output buffer to a new run while an earlier run that writes it may still be in flight. */
+int  wxb_plan_run_async(wxb_plan *plan, const float *emissions_dev, const wxb_outputs *out_dev, void *stream);
+int  wxb_ctx_join(wxb_ctx *ctx, void *stream);
 
 /* One-shot convenience: plan_create + plan_run + plan_destroy, device buffers. */
 int  wxb_align_device(wxb_ctx *ctx, const wxb_batch *batch, const float *emissions_dev,

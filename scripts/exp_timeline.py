@@ -33,7 +33,8 @@ def main():
     rows = rows[:n].astype(np.int64)
     t0 = rows[:, 0].min()
     beg, fwd, end = (rows[:, 0] - t0) / 1e3, (rows[:, 1] - t0) / 1e3, (rows[:, 2] - t0) / 1e3
-    print(f"rows={n} span={end.max():.1f} us  last begin={beg.max():.1f} us")
+    print(f"rows={n} span={end.max():.1f} us  last begin={beg.max():.1f} us  last forward pass done={fwd.max():.1f} us  "
+          f"first walk done={end.min():.1f} us")
     K, T = rows[:, 6], rows[:, 4]
     Wn = np.array([eng._lib.wxb_segment_warps(int(x)) for x in rows[:, 5]])
     KW = Wn * 100 + K

@@ -79,8 +79,11 @@ def test_gpu_matches_port_on_a_long_recording(engine):
 
 @pytest.mark.gpu
 def test_gpu_more_than_64_speakers(engine):
-    """The reference has no speaker limit (groupby): 150 labels go through three launches that carry the
-    running winner; ties (equal overlap, labels in different launches) keep the first label."""
+    """The reference has no speaker limit (groupby): 150 labels go through three launches that carry the running
+    winner.  Expected labels: the reference's own arithmetic (pandas groupby-sum) and, among *exactly* equal sums,
+    the first label — the reference's order among exact ties is whatever numpy's SIMD argsort leaves (it is not
+    stable, and differs between hosts), so queries with a tied maximum are checked against that rule and all the
+    others against the oracle port of the reference."""
     from whisperx_b200 import assign_word_speakers
     rng = np.random.default_rng(11)
     turns = []
@@ -91,11 +94,34 @@ def test_gpu_more_than_64_speakers(engine):
     segs = [{"start": float(a), "end": float(a) + 5.0, "text": "x",
              "words": [{"word": "w", "start": float(a) + 0.5 * k, "end": float(a) + 0.5 * k + 0.4} for k in range(10)]}
             for a in range(0, 300, 5)]
+    df = pd.DataFrame(turns)
+
+    def expected(lo, hi, fill):
+        rows = df.assign(intersection=np.minimum(df["end"], hi) - np.maximum(df["start"], lo))
+        if not fill:
+            rows = rows[rows.intersection > 0]
+        if len(rows) == 0:
+            return None, False
+        g = rows.groupby("speaker")["intersection"].sum()
+        return g.index[int(np.argmax(g.values))], int((g.values == g.values.max()).sum()) > 1
+
+    n_tied = n_plain = 0
+    winners = set()
     for fill in (False, True):
         a = assign_word_speakers(pd.DataFrame(turns), {"segments": copy.deepcopy(segs)}, fill_nearest=fill)
         b = ref_port.speakers_for(pd.DataFrame(turns), {"segments": copy.deepcopy(segs)}, fill)
-        assert a == b
-    assert len({w.get("speaker") for s in a["segments"] for w in s["words"]}) > 64
+        for sa, sb in zip(a["segments"], b["segments"]):
+            for qa, qb in [(sa, sb)] + list(zip(sa["words"], sb["words"])):
+                want, tied = expected(qa["start"], qa["end"], fill)
+                assert qa.get("speaker") == want, (qa, want)
+                winners.add(want)
+                if tied:
+                    n_tied += 1
+                else:
+                    n_plain += 1
+                    assert qa.get("speaker") == qb.get("speaker")
+    assert n_tied > 20 and n_plain > 500
+    assert len(winners) > 64 and any(w is not None and w > "S128" for w in winners)       # labels from all three launches win somewhere
 
 
 @pytest.mark.gpu

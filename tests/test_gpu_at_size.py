@@ -120,3 +120,46 @@ def test_sharded_align_on_two_gpus_equals_single_gpu():
                        cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
     assert "identical to 1 GPU" in p.stdout
+
+
+def test_overlapped_runs_equal_serial_runs(engine):
+    """wxb_plan_run_async keeps two runs in flight (two scratch sets, two groups of side streams): a stream of
+    different batches pushed through it back to back must give, batch for batch, the bytes of the serial path."""
+    from whisperx_b200.engine import _alloc_outputs
+    specs, ems, serial = [], [], []
+    for i, (cfg, n, kind) in enumerate((("c2", 700, "planted"), ("c5", 300, "iid"), ("c2", 64, "iid"), ("c4", 48, "iid"), ("c2", 1500, "iid"))):
+        b = synth.make_batch(n, cfg, align_frames=4, kind=kind, first_segment=1000 * i)
+        spec = BatchSpec(frame_off=b.frame_off, frame_len=b.frame_len, tok_off=b.tok_off, tokens=b.tokens, vocab=b.vocab,
+                         blank_id=b.blank, logits=True, seg_t1=np.zeros(n), seg_ratio=b.durations / b.frame_len)
+        specs.append(spec)
+        ems.append(torch.from_numpy(b.emissions).cuda())
+        serial.append(engine.align_batch(ems[-1], spec).cpu())
+        assert int(serial[-1].status.sum()) == 0
+    fields = ("status", "n_frames", "char_start", "char_end", "char_score", "char_start_s", "char_end_s", "char_score_r")
+    plans = [engine.plan(s) for s in specs]
+    outs = [[_alloc_outputs(s, engine.device, ()) for s in specs] for _ in range(3)]
+    order = [0, 1, 2, 3, 4, 4, 0, 3, 1, 2, 0, 0, 1, 4, 3]
+    for rep in range(3):
+        for o in outs[rep]:
+            for f in ("status", "char_start", "char_end"):
+                getattr(o, f).fill_(-9)
+        for i in order:
+            plans[i].run_overlapped(ems[i], outs[rep][i])
+    engine.join()
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(len(specs)):
+            got = outs[rep][i].cpu()
+            for f in fields:
+                assert torch.equal(getattr(serial[i], f).view(torch.uint8), getattr(got, f).view(torch.uint8)), (rep, i, f)
+    # mixing the two entry points: a serial run in between waits for nothing it should not and corrupts nothing
+    plans[0].run_overlapped(ems[0], outs[0][0])
+    mid = plans[1].run(ems[1])
+    plans[4].run_overlapped(ems[4], outs[0][4])
+    engine.join()
+    torch.cuda.synchronize()
+    for i, got in ((0, outs[0][0].cpu()), (1, mid.cpu()), (4, outs[0][4].cpu())):
+        for f in fields:
+            assert torch.equal(getattr(serial[i], f).view(torch.uint8), getattr(got, f).view(torch.uint8)), (i, f)
+    for p in plans:
+        p.close()

@@ -58,7 +58,7 @@ SYMBOLS = (
     "wxb_plan_run", "wxb_plan_debug_trace", "wxb_align_device", "wxb_align_host", "wxb_log_softmax_device",
     "wxb_backtrack_trellis_device", "wxb_round3", "wxb_round3_np", "wxb_pairwise_sum", "wxb_tokens_per_lane",
     "wxb_segment_warps", "wxb_set_k_target", "wxb_assign_speakers_device", "wxb_assign_speakers_host",
-    "wxb_set_chunk_bytes", "wxb_exact_scores_host",
+    "wxb_set_chunk_bytes", "wxb_exact_scores_host", "wxb_plan_run_async", "wxb_ctx_join",
 )
 
 _LIB = None
@@ -88,6 +88,10 @@ def load(build_if_missing: bool = True):
     L.wxb_plan_launch_count.argtypes = [vp]
     L.wxb_plan_stats.argtypes = [vp, i64p, i64p, i64p]
     L.wxb_plan_run.argtypes = [vp, vp, C.POINTER(Outputs), vp, f32p]
+    L.wxb_plan_run_async.argtypes = [vp, vp, C.POINTER(Outputs), vp]
+    L.wxb_plan_run_async.restype = C.c_int
+    L.wxb_ctx_join.argtypes = [vp, vp]
+    L.wxb_ctx_join.restype = C.c_int
     L.wxb_plan_debug_trace.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int64]
     L.wxb_plan_debug_trace.restype = C.c_int
     L.wxb_align_device.argtypes = [vp, C.POINTER(Batch), vp, C.POINTER(Outputs), vp]

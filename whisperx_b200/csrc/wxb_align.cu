@@ -93,6 +93,36 @@ struct Arena {
     void release() { release_mem(); if (uploaded) cudaEventDestroy(uploaded); uploaded = nullptr; }
 };
 
+// Everything one run of a plan needs for itself: the scratch the kernels write (choice bits, exp(logp[t,0]), row
+// statistics of the fused log-softmax ...), the side streams its classes run on and the events that fork / join
+// them.  A ctx has two, so that two runs can be in flight at once (wxb_plan_run_async): the tail of one batch —
+// its last, longest segments draining the GPU — overlaps the head of the next.
+struct RunSlot {
+    DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, wide_lp;
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
+    cudaEvent_t done = nullptr;               // the last run that used this slot has finished (scratch reusable, results complete)
+    cudaStream_t done_on = nullptr;           // stream `done` was last recorded on (a later run on that stream need not wait)
+    cudaError_t create() {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+        return e;
+    }
+    void destroy() {
+        DevBuf *bufs[] = {&bits, &p0, &rowmax, &rowlse, &wild, &nframes_scratch, &wide_lp};
+        for (DevBuf *b : bufs) b->release();
+        for (int i = 0; i < NSIDE; ++i) {
+            if (side[i]) cudaStreamDestroy(side[i]);
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (done) cudaEventDestroy(done);
+    }
+};
+
 struct wxb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -100,14 +130,14 @@ struct wxb_ctx {
     cudaStream_t copy = nullptr;              // host->device emission chunks (wxb_align_host)
     cudaStream_t d2h = nullptr;               // per-chunk word reduction + device->host result copies (wxb_align_host)
     cudaEvent_t ev_d2h = nullptr;
-    cudaEvent_t ev_busy = nullptr;            // end of the last wxb_plan_run of this ctx (runs share the scratch)
-    cudaStream_t last_run_stream = nullptr;
+    cudaStream_t jstream = nullptr;           // joins the side streams of an overlapped run (wxb_plan_run_async)
     cudaEvent_t ev_dbg[3] = {};               // WXB_DEBUG_TIMING: kernels joined / results on the host / per-chunk
-    cudaStream_t side[NSIDE] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    RunSlot slot[2];                          // [0]: wxb_plan_run / wxb_align_host; overlapped runs alternate between the two
+    int next_async = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<cudaEvent_t> ev_chunk;        // one per emission chunk in flight
     std::vector<cudaEvent_t> ev_soft;         // wide-vocabulary logits: chunk normalised
-    DevBuf bits, p0, rowmax, rowlse, wild, nframes_scratch, trace, wide_lp, spk_best;
+    DevBuf trace, spk_best;
     int side_streams = NSIDE;                 // WXB_SIDE_STREAMS (1..NSIDE)
     int k_target = 0;                         // WXB_K_TARGET / wxb_ctx_set_k_target: 0 = process default, then per batch
     int tile_pref = 32;                       // WXB_TILE_FRAMES (experiments): largest tile length tried
@@ -277,11 +307,9 @@ extern "C" int wxb_create(int device, wxb_ctx **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->jstream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = c->slot[i].create();
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev_dbg[i]);
-    for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < NSIDE && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
     if (e != cudaSuccess) {
@@ -296,7 +324,9 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->trace, &c->bits, &c->p0, &c->rowmax, &c->rowlse, &c->wild, &c->nframes_scratch, &c->wide_lp, &c->spk_best, &c->h_emis, &c->h_path_tok};
+    DevBuf *bufs[] = {&c->trace, &c->spk_best, &c->h_emis, &c->h_path_tok};
+    for (RunSlot &sl : c->slot) sl.destroy();
+    if (c->jstream) cudaStreamDestroy(c->jstream);
     for (DevBuf *b : bufs) b->release();
     for (auto &b : c->h_i32) b.release();
     for (auto &b : c->h_f64) b.release();
@@ -308,13 +338,7 @@ extern "C" void wxb_destroy(wxb_ctx *c) {
     if (c->copy) cudaStreamDestroy(c->copy);
     if (c->d2h) cudaStreamDestroy(c->d2h);
     if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
-    if (c->ev_busy) cudaEventDestroy(c->ev_busy);
     for (int i = 0; i < 3; ++i) if (c->ev_dbg[i]) cudaEventDestroy(c->ev_dbg[i]);
-    for (int i = 0; i < NSIDE; ++i) {
-        if (c->side[i]) cudaStreamDestroy(c->side[i]);
-        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
-    }
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     delete c;
@@ -611,7 +635,10 @@ extern "C" void wxb_plan_destroy(wxb_plan *plan) {
     cudaSetDevice(plan->ctx->device);
     // the arena goes back to the pool: nothing may still be reading it
     if (plan->arena && plan->arena->uploaded) cudaEventSynchronize(plan->arena->uploaded);
-    if (plan->ran) cudaStreamSynchronize(plan->last_stream);
+    if (plan->ran) {
+        cudaStreamSynchronize(plan->last_stream);
+        for (RunSlot &sl : plan->ctx->slot) cudaEventSynchronize(sl.done);       // overlapped runs end on the join stream
+    }
     plan_free(plan);
 }
 
@@ -684,8 +711,11 @@ struct HostSink {
     const int64_t *tok_off, *word_off, *frame_off;
 };
 
+// slot_i: which RunSlot (scratch + side streams) the run uses.  overlapped: do not make `st` wait for the run —
+// the side streams are joined on the ctx's join stream instead, where the slot's `done` event is recorded
+// (wxb_plan_run_async / wxb_ctx_join); every class then goes to a side stream, also when there is only one.
 static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_ready, const wxb_outputs *o, cudaStream_t st,
-                    float *elapsed_dp_ms, const HostSink *sink = nullptr) {
+                    float *elapsed_dp_ms, const HostSink *sink = nullptr, int slot_i = 0, bool overlapped = false) {
     if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
     if (pl->S == 0) { if (elapsed_dp_ms) *elapsed_dp_ms = 0.f; return WXB_OK; }
     if (!o->status || !o->char_start || !o->char_end || !o->char_score)
@@ -711,27 +741,28 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     const bool wide_logits = logits && (pl->V > wxb::WIDE_V || (pl->V & 1) == 0);
 
     wxb_ctx *c = pl->ctx;
+    RunSlot &sl = c->slot[slot_i];
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(c->bits.ensure(static_cast<size_t>(std::max<long long>(pl->bits_words, 1)) * 4));
-    CUDA_TRY(c->p0.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
-    if (pl->has_wild) CUDA_TRY(c->wild.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+    CUDA_TRY(sl.bits.ensure(static_cast<size_t>(std::max<long long>(pl->bits_words, 1)) * 4));
+    CUDA_TRY(sl.p0.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+    if (pl->has_wild) CUDA_TRY(sl.wild.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
     float *wide_dst = nullptr;
     if (wide_logits) {
         if (o->logprobs) wide_dst = o->logprobs;
         else if (chunk_ready || (pl->flags & WXB_F_CLOBBER)) wide_dst = const_cast<float *>(emis);   // c->h_emis (ours), or the caller's scratch
         else {
-            CUDA_TRY(c->wide_lp.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * pl->V * 4));
-            wide_dst = c->wide_lp.as<float>();
+            CUDA_TRY(sl.wide_lp.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * pl->V * 4));
+            wide_dst = sl.wide_lp.as<float>();
         }
     }
     if (logits && !wide_logits) {
-        CUDA_TRY(c->rowmax.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
-        CUDA_TRY(c->rowlse.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+        CUDA_TRY(sl.rowmax.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
+        CUDA_TRY(sl.rowlse.ensure(static_cast<size_t>(std::max<int64_t>(pl->sum_T, 1)) * 4));
     }
     int *nframes = o->n_frames;
     if (!nframes) {
-        CUDA_TRY(c->nframes_scratch.ensure(static_cast<size_t>(pl->S) * 4));
-        nframes = c->nframes_scratch.as<int>();
+        CUDA_TRY(sl.nframes_scratch.ensure(static_cast<size_t>(pl->S) * 4));
+        nframes = sl.nframes_scratch.as<int>();
     }
 
     Params P;
@@ -739,11 +770,11 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     P.emis = emis;
     P.tok4 = pl->d_tok4;
     P.segs = pl->d_segs;
-    P.bits = c->bits.as<uint32_t>();
-    P.p0 = c->p0.as<float>();
-    P.rowmax = c->rowmax.as<float>();
-    P.rowlse = c->rowlse.as<float>();
-    P.wild = c->wild.as<float>();
+    P.bits = sl.bits.as<uint32_t>();
+    P.p0 = sl.p0.as<float>();
+    P.rowmax = sl.rowmax.as<float>();
+    P.rowlse = sl.rowlse.as<float>();
+    P.wild = sl.wild.as<float>();
     P.V = pl->V; P.blank = pl->blank; P.is_logits = (logits && !wide_logits) ? 1 : 0;
     if (wide_logits) P.emis = wide_dst;
     P.status = o->status; P.nframes = nframes;
@@ -797,8 +828,11 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
             rows_ready = c->ev_soft.data();
         }
     }
-    // every class's backtrack_kernel and finalize_kernel follow its align_kernel on the same stream, so
-    // they overlap the other classes' recurrences instead of running after all of them
+    // every class's backtrack_kernel and finalize_kernel follow its align_kernel on the same stream.  The block
+    // scheduler places CTAs in launch order, so the small walk kernels of the early classes queue behind the later
+    // align_kernel launches and run near the end of the step (timeline, profiles/r2_timeline.md); moving them to
+    // highest-priority companion streams made them start as soon as their class was done but moved the end of the
+    // step by nothing (0.543 vs 0.516 ms: the walks cost their issue slots wherever they run) — not kept.
     auto finalize = [&](const Bucket &b, cudaStream_t s) -> cudaError_t {
         backtrack_kernel<<<(b.count + 3) / 4, 128, 0, s>>>(P, b.first, b.count);
         if (b.fin_count > 0) finalize_kernel<<<b.fin_count, 128, 0, s>>>(P, pl->d_fin + b.fin_first);
@@ -819,22 +853,22 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
             o->char_end_s, o->char_score_r, o->word_start_s + w0, o->word_end_s + w0, o->word_score + w0);
         return cudaGetLastError();
     };
-    if (nb == 1 && !chunk_ready) {
+    if (nb == 1 && !chunk_ready && !overlapped) {
         const Bucket &b = pl->buckets[0];
         CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, st, debug, pl->has_wild));
         CUDA_TRY(finalize(b, st));
     } else if (nb >= 1) {
         // classes are independent: fork onto side streams so that every SM sees a mix of them
         const int used = std::min(nb, c->side_streams);
-        CUDA_TRY(cudaEventRecord(c->ev_fork, st));
-        for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
-        if (sink) CUDA_TRY(cudaStreamWaitEvent(c->d2h, c->ev_fork, 0));
+        CUDA_TRY(cudaEventRecord(sl.ev_fork, st));
+        for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamWaitEvent(sl.side[i], sl.ev_fork, 0));
+        if (sink) CUDA_TRY(cudaStreamWaitEvent(c->d2h, sl.ev_fork, 0));
         int seen_chunk[NSIDE];
         for (int i = 0; i < NSIDE; ++i) seen_chunk[i] = -1;
         auto drain_chunk = [&](int chunk) -> int {      // results of the chunk's segments -> host, on the d2h stream
             for (int i = 0; i < used; ++i) {
-                CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));
-                CUDA_TRY(cudaStreamWaitEvent(c->d2h, c->ev_join[i], 0));
+                CUDA_TRY(cudaEventRecord(sl.ev_join[i], sl.side[i]));
+                CUDA_TRY(cudaStreamWaitEvent(c->d2h, sl.ev_join[i], 0));
             }
             const int64_t s0 = pl->chunk_seg[chunk], s1 = pl->chunk_seg[chunk + 1];
             if (s1 <= s0) return WXB_OK;
@@ -864,11 +898,11 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
                 cur_chunk = b.chunk;
             }
             if (rows_ready && seen_chunk[si] < b.chunk) {
-                CUDA_TRY(cudaStreamWaitEvent(c->side[si], rows_ready[b.chunk], 0));
+                CUDA_TRY(cudaStreamWaitEvent(sl.side[si], rows_ready[b.chunk], 0));
                 seen_chunk[si] = b.chunk;
             }
-            CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, c->side[si], debug, pl->has_wild));
-            CUDA_TRY(finalize(b, c->side[si]));
+            CUDA_TRY(launch_align(b.K, b.W, b.NB, b.TE, P, b.first, b.count, b.smem, sl.side[si], debug, pl->has_wild));
+            CUDA_TRY(finalize(b, sl.side[si]));
         }
         if (sink) {
             const int n_chunks = static_cast<int>(pl->chunk_seg.size()) - 1;
@@ -876,9 +910,10 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
             CUDA_TRY(cudaEventRecord(c->ev_dbg[1], c->d2h));
             CUDA_TRY(cudaEventRecord(c->ev_d2h, c->d2h));
         }
+        cudaStream_t joiner = overlapped ? c->jstream : st;
         for (int i = 0; i < used; ++i) {
-            CUDA_TRY(cudaEventRecord(c->ev_join[i], c->side[i]));
-            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[i], 0));
+            CUDA_TRY(cudaEventRecord(sl.ev_join[i], sl.side[i]));
+            CUDA_TRY(cudaStreamWaitEvent(joiner, sl.ev_join[i], 0));
         }
         if (sink) {
             CUDA_TRY(cudaEventRecord(c->ev_dbg[0], st));          // all kernels done
@@ -886,6 +921,16 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
         }
     }
     if (elapsed_dp_ms) CUDA_TRY(cudaEventRecord(c->ev_t1, st));
+    if (overlapped) {
+        // the join stream has waited for every class; order it after this call's own work on `st` too (the records of
+        // un-alignable segments, a plan without classes), reduce the words there and publish the slot's `done`
+        if (nb == 0) { CUDA_TRY(cudaEventRecord(sl.ev_fork, st)); }
+        CUDA_TRY(cudaStreamWaitEvent(c->jstream, sl.ev_fork, 0));
+        CUDA_TRY(reduce_words(0, pl->W, c->jstream));
+        CUDA_TRY(cudaEventRecord(sl.done, c->jstream));
+        sl.done_on = c->jstream;
+        return WXB_OK;
+    }
     if (!sink) CUDA_TRY(reduce_words(0, pl->W, st));
     if (elapsed_dp_ms) {
         CUDA_TRY(cudaEventSynchronize(c->ev_t1));
@@ -894,14 +939,11 @@ static int run_impl(wxb_plan *pl, const float *emis, const cudaEvent_t *chunk_re
     return WXB_OK;
 }
 
-// A plan that is run again and again on the same buffers (steady-state serving, bench.py) is a fixed
-// DAG of ~25 launches over 8 side streams joined by events: from the third identical call on it is
-// replayed as one CUDA graph, which removes the per-step event/launch latencies between steps.
 static int plan_run_unserialised(wxb_plan *pl, const float *emis, const wxb_outputs *o, cudaStream_t st, float *elapsed_dp_ms);
 
-// All plans of a ctx share its scratch (choice bits, p0, ...) and side streams: two runs in flight on different
-// caller streams would race on them.  Every run therefore waits for the previous run of the same ctx (an event
-// recorded at its end) before it starts — a no-op when the caller uses one stream, which is the fast case.
+// The scratch of a RunSlot is shared by every plan that runs in it: a run first makes its stream wait (on the
+// device) for the slot's previous run, whatever stream that was enqueued on, and publishes its own end in the
+// slot's `done` event.  wxb_plan_run always uses slot 0 (a no-op wait when the caller keeps to one stream).
 extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *o, void *stream_, float *elapsed_dp_ms) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run: NULL argument");
@@ -910,13 +952,47 @@ extern "C" int wxb_plan_run(wxb_plan *pl, const float *emis, const wxb_outputs *
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(st, &cap));
     const bool serialise = cap == cudaStreamCaptureStatusNone && pl->S > 0;
-    if (serialise && c->last_run_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_busy, 0));
+    RunSlot &sl = c->slot[0];
+    if (serialise && sl.done_on != st) CUDA_TRY(cudaStreamWaitEvent(st, sl.done, 0));
     const int rc = plan_run_unserialised(pl, emis, o, st, elapsed_dp_ms);
     if (serialise && rc == WXB_OK) {
-        CUDA_TRY(cudaEventRecord(c->ev_busy, st));
-        c->last_run_stream = st;
+        CUDA_TRY(cudaEventRecord(sl.done, st));
+        sl.done_on = st;
     }
     return rc;
+}
+
+// Overlapped run: same work as wxb_plan_run, but `stream` is not made to wait for it.  Consecutive calls
+// alternate between the ctx's two RunSlots (own scratch, own side streams), so at most two runs are in flight:
+// call n+2 waits, on the device, for call n.  The tail of a batch — its last, longest segments, when most SMs
+// have nothing left to do — is filled by the head of the next one.  Results are complete once wxb_ctx_join()'s
+// stream has passed the join; the caller must not reuse output buffers of a run that may still be in flight.
+extern "C" int wxb_plan_run_async(wxb_plan *pl, const float *emis, const wxb_outputs *o, void *stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (!pl || !o) return fail(WXB_EINVAL, "wxb_plan_run_async: NULL argument");
+    if (pl->S == 0) return WXB_OK;
+    wxb_ctx *c = pl->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return fail(WXB_EUNSUPPORTED, "wxb_plan_run_async: the stream is being captured");
+    if (o->trellis || o->final_col || c->want_trace) return fail(WXB_EUNSUPPORTED, "wxb_plan_run_async: debug outputs need wxb_plan_run");
+    const int si = c->next_async;
+    c->next_async ^= 1;
+    RunSlot &sl = c->slot[si];
+    CUDA_TRY(cudaStreamWaitEvent(st, sl.done, 0));          // the run that used this slot two calls ago
+    const int rc = run_impl(pl, emis, nullptr, o, st, nullptr, nullptr, si, /*overlapped=*/true);
+    if (rc == WXB_OK) pl->last_stream = c->jstream;
+    return rc;
+}
+
+extern "C" int wxb_ctx_join(wxb_ctx *c, void *stream_) {
+    if (!c) return fail(WXB_EINVAL, "wxb_ctx_join: ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    for (RunSlot &sl : c->slot)
+        if (sl.done_on != st) CUDA_TRY(cudaStreamWaitEvent(st, sl.done, 0));
+    return WXB_OK;
 }
 
 // A plan that is run again and again on the same buffers (steady-state serving, bench.py) is a fixed
@@ -936,7 +1012,8 @@ static int plan_run_unserialised(wxb_plan *pl, const float *emis, const wxb_outp
     ++pl->graph_same;
     if (pl->graph_same < 3) return run_impl(pl, emis, nullptr, o, st, nullptr);      // eager: allocates scratch, configures kernels
     CUDA_TRY(cudaSetDevice(c->device));
-    void *scratch[7] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p, c->wide_lp.p};
+    const RunSlot &s0 = c->slot[0];
+    void *scratch[7] = {s0.bits.p, s0.p0.p, s0.rowmax.p, s0.rowlse.p, s0.wild.p, s0.nframes_scratch.p, s0.wide_lp.p};
     if (pl->graph_exec && memcmp(scratch, pl->graph_scratch, sizeof scratch) != 0) {
         cudaGraphExecDestroy(pl->graph_exec);     // a larger plan regrew the shared scratch since the capture
         pl->graph_exec = nullptr;
@@ -960,7 +1037,7 @@ static int plan_run_unserialised(wxb_plan *pl, const float *emis, const wxb_outp
             pl->graph_off = true;
             return run_impl(pl, emis, nullptr, o, st, nullptr);
         }
-        void *now[7] = {c->bits.p, c->p0.p, c->rowmax.p, c->rowlse.p, c->wild.p, c->nframes_scratch.p, c->wide_lp.p};
+        void *now[7] = {s0.bits.p, s0.p0.p, s0.rowmax.p, s0.rowlse.p, s0.wild.p, s0.nframes_scratch.p, s0.wide_lp.p};
         memcpy(pl->graph_scratch, now, sizeof now);
     }
     pl->last_stream = st;

@@ -506,7 +506,6 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                 const float s3 = src; step(e4.w, l4.w, w4.w);
                 if (lane == laneN) sts_f32x4(left_out, s0, s1, s2, s3);    // rows t..t+3 of my last column -> warp wi+1
                 eb_in += 16u; left_in += 16u; left_out += 16u; wild_in += 16u;
-                flush_if_word_done();
             }
             for (; tt < n; ++tt) {             // the last, partial block of a segment
                 const float eb = lds_f32(eb_in), lv = lds_f32(left_in);
@@ -514,8 +513,11 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                 if (lane == laneN) sts_f32(left_out, src);
                 step(eb, lv, wv);
                 eb_in += 4u; left_in += 4u; left_out += 4u; wild_in += 4u;
-                flush_if_word_done();
             }
+            // tiles are 32, 16, 8 or 4 frames long and start at multiples of their length: a 32-frame choice word
+            // can only end where a tile ends, so the check sits here and not in the frame loop (six predicated
+            // instructions per four frames otherwise)
+            flush_if_word_done();
             __syncwarp();
             // hand the tile on: boundary values to warp wi+1, or the buffer back to the producer
             if (lane == 0) mbar_arrive(next_bar0 + 8u * b);

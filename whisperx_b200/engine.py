@@ -199,6 +199,18 @@ class Plan:
             out.extra["dp_ms"] = ms.value
         return out
 
+    def run_overlapped(self, emissions: torch.Tensor, out: BatchResult) -> BatchResult:
+        """wxb_plan_run_async: enqueue the batch without making the current stream wait for it; up to two such
+        runs are in flight per engine (the tail of one batch overlaps the head of the next).  Call
+        `engine.join()` before reading `out` (and before handing `out` to a third run)."""
+        eng = self.engine
+        eng._check_emissions(emissions, self.spec)
+        co = out.to_c()
+        with eng._lock, torch.cuda.device(eng.device):
+            stream = torch.cuda.current_stream(eng.device).cuda_stream
+            N.check(eng._lib.wxb_plan_run_async(self._h, emissions.data_ptr(), C.byref(co), stream), "wxb_plan_run_async")
+        return out
+
     def close(self):
         if self._h:
             with self.engine._lock:
@@ -260,6 +272,11 @@ class AlignEngine:
     # ---- hot path
     def plan(self, spec: BatchSpec) -> Plan:
         return Plan(self, spec)
+
+    def join(self) -> None:
+        """Make the current stream wait for every overlapped run of this engine (wxb_ctx_join)."""
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.wxb_ctx_join(self._ctx, torch.cuda.current_stream(self.device).cuda_stream), "wxb_ctx_join")
 
     def align_batch(self, emissions: torch.Tensor, spec: BatchSpec, want: Sequence[str] = ()) -> BatchResult:
         """get_trellis + backtrack + merge_repeats (+ timestamps / words) for every segment."""
