@@ -226,10 +226,12 @@ double wxb_round3_np(double x);                           /* np.float64.__round_
 double wxb_pairwise_sum(const double *a, int64_t n);      /* numpy add.reduce order (alignment.py:308) */
 int    wxb_tokens_per_lane(int32_t n_tokens);             /* K (token columns per lane) for N tokens, <=0 if unsupported */
 int    wxb_segment_warps(int32_t n_tokens);               /* W (compute warps of the segment's CTA), <=0 if unsupported */
-/* Planner knob: a segment gets the fewest warps that keep K <= k_target.  By default (0) the planner picks
- * 5 or 8 per batch (short tails vs fewest issue slots); 1..8 forces a value, -1 restores the default,
- * 0 only queries.  Returns the previous value.  Process-wide; affects plans created afterwards.
- * wxb_tokens_per_lane / wxb_segment_warps answer for the forced value, or for 5 when none is forced. */
+/* Planner knob: every segment of a batch runs with K = k_target token columns per lane in its full warps (one
+ * kernel instantiation per batch; the last warp of a segment holds what is left with KL <= K columns per lane).
+ * By default (0) the planner picks per batch: 8 for vocabularies >= 64, else 6, or 3 when the batch is too small to
+ * fill the GPU; 1..8 forces a value, -1 restores the default, 0 only queries.  Returns the previous value.
+ * Process-wide default (atomic); a ctx created with WXB_K_TARGET set keeps its own.  wxb_tokens_per_lane /
+ * wxb_segment_warps answer for the forced value, or for 4 when none is forced. */
 int    wxb_set_k_target(int k_target);
 
 #ifdef __cplusplus

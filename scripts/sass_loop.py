@@ -4,7 +4,7 @@ K = sys.argv[1]
 show_all = len(sys.argv) > 2
 ins = []
 for l in open(f'/tmp/k{K}.sass'):
-    m = re.match(r'\s*/\*([0-9a-f]{4})\*/\s*(.*?);', l)
+    m = re.match(r'\s*/\*([0-9a-f]{4,5})\*/\s*(.*?);', l)
     if m: ins.append((int(m.group(1), 16), m.group(2).strip()))
 addr = {a: i for i, (a, _) in enumerate(ins)}
 for i, (a, t) in enumerate(ins):

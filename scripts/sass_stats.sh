@@ -5,13 +5,13 @@ set -e
 cd "$(dirname "$0")/.."
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -I include "$@" -cubin -o /tmp/wxb_inst.cubin whisperx_b200/csrc/wxb_inst.cu
 for K in 1 2 3 4 5 6 7 8; do
-  cuobjdump -sass -fun "_ZN3wxb12align_kernelILi${K}ELb0ELb0EEEvNS_6ParamsEiii" /tmp/wxb_inst.cubin | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's#/\* 0x[0-9a-f]+ \*/##' > /tmp/k$K.sass
+  cuobjdump -sass -fun "_ZN3wxb12align_kernelILi${K}ELb0ELb0EEEvNS_6ParamsEiii" /tmp/wxb_inst.cubin | grep -E "^\s+/\*[0-9a-f]{4,5}\*/" | sed -E 's#/\* 0x[0-9a-f]+ \*/##' > /tmp/k$K.sass
   python3 - $K <<'PY'
 import re, sys
 K=sys.argv[1]
 ins=[]
 for l in open(f'/tmp/k{K}.sass'):
-    m=re.match(r'\s*/\*([0-9a-f]{4})\*/\s*(.*?);', l)
+    m=re.match(r'\s*/\*([0-9a-f]{4,5})\*/\s*(.*?);', l)
     if m: ins.append((int(m.group(1),16), m.group(2).strip()))
 addr={a:i for i,(a,_) in enumerate(ins)}
 out=[]

@@ -81,13 +81,15 @@ def test_tokens_per_lane_buckets():
     assert lib.wxb_set_k_target(0) == 0                    # default: chosen per batch
     lib.wxb_set_k_target(6)
     assert shape(0) == (0, 0)
+    # every full warp holds K = k_target columns per lane; the last warp of a segment what is left
     assert shape(1) == (1, 1) and shape(32) == (1, 1) and shape(33) == (1, 2) and shape(192) == (1, 6)
-    assert shape(193) == (2, 4) and shape(384) == (2, 6) and shape(400) == (3, 5) and shape(2048) == (11, 6)
+    assert shape(193) == (2, 6) and shape(384) == (2, 6) and shape(400) == (3, 6) and shape(2048) == (11, 6)
+    assert shape(31 * 32 * 6) == (31, 6) and shape(31 * 32 * 6 + 1) == (27, 7)      # too long for 31 warps of 6: a K of its own
     assert shape(31 * 32 * 8) == (31, 8) and shape(31 * 32 * 8 + 1) == (-1, -1)
     assert lib.wxb_set_k_target(4) == 6
-    assert shape(128) == (1, 4) and shape(129) == (2, 3) and shape(400) == (4, 4)
+    assert shape(128) == (1, 4) and shape(129) == (2, 4) and shape(400) == (4, 4)
     assert lib.wxb_set_k_target(-1) == 4 and lib.wxb_set_k_target(0) == 0
-    assert shape(160) == (1, 5) and shape(161) == (2, 3) and shape(400) == (3, 5)
+    assert shape(128) == (1, 4) and shape(161) == (2, 4) and shape(400) == (4, 4)      # unforced: the helpers answer for K = 4
 
 
 def test_no_cpu_fallback():

@@ -188,47 +188,54 @@ struct wxb_plan {
 // wxb_create) and falls back to this one, so contexts on different devices / threads share no mutable planner state.
 static std::atomic<int> g_k_target{0};        // 0 = chosen per batch (see pick_k_target); 1..KMAX = forced
 
-// Few columns per lane (more warps per segment) shorten a segment's latency, which is what bounds a
-// batch whose longest segments are a large part of the makespan; many columns per lane spend fewer
-// issue slots per cell, which is what bounds a batch that fills the GPU several times over.
-// frames_x_warps(kt) / capacity is the number of frame-times the batch needs at k_target kt; if that
-// is at least twice the longest segment, the tail does not matter and the efficient shape wins.
-// With a wide vocabulary the single producer warp's log-softmax (~11 issue slots per symbol per frame)
-// costs as much per tile as a 5-column compute warp: the wavefront then runs at the producer's pace
-// and fewer, wider compute warps do the same work with fewer issue slots (measured on C4, V = 100:
-// k_target 8 is 12 % faster than 5).
+// The batch's K (columns per lane of every full warp).  Measured on B200 with the uniform-K planner
+// (bench.py --only-main, WXB_K_TARGET sweep, profiles/r2_k_sweep.md): the 4,096-segment VAD-cut batch runs
+// 0.50 / 0.47 / 0.49 / 0.46 / 0.45 / 0.46 / 0.50 ms for K = 2 .. 8, all-30-s batches 0.90 / 0.84 / 0.85 / 0.85 ms for
+// K = 4 / 5 / 6 / 8, the V = 100 long-transcript batch 1.00 / 0.91 / 0.89 ms for K = 4 / 6 / 8: more columns per lane
+// spend fewer issue slots per cell (the per-frame overhead is shared by more columns) until the 64 registers
+// of K >= 7 cost residency.  A batch too small to fill the GPU gets short wavefronts (more warps per segment)
+// instead: its segments' own latency is then all that matters.
 static int pick_k_target(const int64_t *tok_off, const int64_t *frame_off, const int32_t *frame_len, int64_t S, int sm_count, int V) {
-    const int kt_wide = KMAX, kt_narrow = 5;
-    if (V >= 64) return kt_wide;
-    double work = 0.0;
-    long long tmax = 0;
+    if (V >= 64) return KMAX;
+    const int k_big = 6, k_small = 3;
+    long long warps = 0;
     for (int64_t s = 0; s < S; ++s) {
         const long long n = tok_off[s + 1] - tok_off[s];
         const long long t = frame_len ? frame_len[s] : frame_off[s + 1] - frame_off[s];
         if (n <= 0 || n > t) continue;
-        work += static_cast<double>(t) * static_cast<double>((n + 32 * kt_wide - 1) / (32 * kt_wide));
-        tmax = std::max(tmax, t);
+        warps += (n + 32 * k_big - 1) / (32 * k_big) + 1;
     }
-    const double capacity = 24.0 * sm_count;          // resident compute warps
-    return (tmax > 0 && work / capacity >= 2.0 * static_cast<double>(tmax)) ? kt_wide : kt_narrow;
+    return warps >= 4ll * sm_count ? k_big : k_small;
 }
 
-static bool shape_of(long long n, int *W, int *K, int k_target = 0) {
+// -> W compute warps, K columns per lane in the full warps (0 .. W-2), KL <= K in the last one (wxb_kernel.cuh).
+// Every segment of a batch gets the batch's K (k_target) — one align_kernel instantiation, one recurrence loop
+// body for all full warps: the instruction cache is what separates a fast batch from a slow one here (the same
+// step with two or three instantiations co-resident on an SM runs 10-20 % slower).  Only a transcript too long
+// for 31 warps of K columns gets a larger K of its own.
+static bool shape_of(long long n, int *W, int *K, int k_target = 0, int *KL = nullptr) {
     if (n <= 0) return false;
-    if (k_target <= 0) { const int g = g_k_target.load(std::memory_order_relaxed); k_target = g > 0 ? g : 5; }
-    long long w = (n + 32ll * k_target - 1) / (32ll * k_target);
-    if (w > WMAX) w = WMAX;
-    const long long k = (n + 32 * w - 1) / (32 * w);
-    if (k > KMAX) return false;
+    if (k_target <= 0) { const int g = g_k_target.load(std::memory_order_relaxed); k_target = g > 0 ? g : 4; }
+    long long k = k_target;
+    long long w = (n + 32 * k - 1) / (32 * k);
+    if (w > WMAX) {
+        k = (n + 32ll * WMAX - 1) / (32ll * WMAX);
+        if (k > KMAX) return false;
+        w = (n + 32 * k - 1) / (32 * k);
+    }
+    const long long m = n - 32 * k * (w - 1);             // 1 .. 32K columns left for the last warp
     *W = static_cast<int>(w);
     *K = static_cast<int>(k);
+    if (KL) *KL = static_cast<int>((m + 31) / 32);
     return true;
 }
 
+// most token columns any lane of the segment's CTA holds
 static int tokens_per_lane(long long n) {
-    int W, K;
+    int W, K, KL;
     if (n <= 0) return 0;
-    return shape_of(n, &W, &K) ? K : -1;
+    if (!shape_of(n, &W, &K, 0, &KL)) return -1;
+    return W == 1 ? KL : K;
 }
 
 // Frames per shared-memory tile (cp.async.bulk needs 16-byte multiples, i.e. TE % 4 == 0): 32 when the
@@ -469,8 +476,8 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, const std::vector
         for (; chunk_prev < chunk; ++chunk_prev) pl->chunk_seg[chunk_prev + 1] = s;
         const long long this_trellis = trellis_off;
         trellis_off += static_cast<long long>(T + 1) * (N + 1);
-        int K = -1, Wc = 0;
-        const bool fits = shape_of(N, &Wc, &K, k_target);
+        int K = -1, Wc = 0, KL = 0;
+        const bool fits = shape_of(N, &Wc, &K, k_target, &KL);
         if (N == 0 || (N > T && (!no_shortcut || !fits))) {
             shorts.push_back({to[s], fo[s], N, T, static_cast<int>(s), 0});
             continue;
@@ -483,7 +490,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, const std::vector
         d.tok_base = to[s];
         d.bits_off = 0;
         d.trellis_off = this_trellis;
-        d.T = T; d.N = N; d.seg = static_cast<int>(s); d.K = K; d.W = Wc; d.pad = chunk;
+        d.T = T; d.N = N; d.seg = static_cast<int>(s); d.K = K; d.W = Wc; d.pad = chunk; d.KL = KL; d.pad2 = 0;
         wmax = std::max(wmax, Wc);
         descs.push_back(d);
         pl->cells += static_cast<long long>(T) * N;
@@ -515,7 +522,7 @@ static int plan_create_impl(wxb_ctx *ctx, const wxb_batch *bt, const std::vector
             pl->buckets.push_back(b);
         }
         pl->buckets.back().count += 1;
-        pl->buckets.back().cost += static_cast<long long>(descs[i].T) * descs[i].K * descs[i].W;
+        pl->buckets.back().cost += static_cast<long long>(descs[i].T) * (descs[i].K * (descs[i].W - 1) + descs[i].KL);
         pl->buckets.back().fin_count += (descs[i].N + 127) / 128;
         fin_next += (descs[i].N + 127) / 128;
     }

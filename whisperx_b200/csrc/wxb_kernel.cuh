@@ -8,9 +8,12 @@
 //   merge_repeats          whisperx/alignment.py:438-454  (finalize_kernel: per-token start/end/mean prob)
 //   char timestamps        whisperx/alignment.py:252-264  (finalize_kernel: exact decimal rounding)
 //
-// CTA = W compute warps + 1 producer warp.  Global lane g = 32*w + lane owns K (g < r) or K-1
-// (g >= r) consecutive token columns, K = ceil(N / 32W) <= 8, so every lane of every warp holds real
-// columns and the last column of the transcript is always the last column of lane 31 of warp W-1.
+// CTA = W compute warps + 1 producer warp.  Warps 0 .. W-2 are "full": every lane owns K consecutive token
+// columns (K = ceil(N / 32 W0) <= 8 for the planner's first guess W0, then W = ceil(N / 32K)).  The last warp
+// holds the m = N - 32K(W-1) columns that remain (1 <= m <= 32K) with KL = ceil(m / 32) <= K columns per lane:
+// its first rL = m - 32(KL-1) lanes own KL columns, the others KL-1, so the last column of the transcript is
+// the last column of its last occupied lane.  The recurrence loop is instantiated per column count: a
+// transcript of 399 tokens runs as 160 + 160 + 96 column slots (K = 5, KL = 3) instead of 3 x 160.
 //
 //   producer warp   streams the segment's emission rows HBM -> shared memory exactly once, TE frames
 //                   per tile through a ring of NB buffers (one cp.async.bulk per tile, mbarrier
@@ -41,8 +44,9 @@ struct SegDesc {
     long long tok_base;     // tok_off[s]:   index base for tokens and per-char outputs
     long long bits_off;     // 32-bit word offset into the choice-bit scratch
     long long trellis_off;  // float offset into the debug trellis (DEBUG only)
-    int T, N, seg, K;
-    int W, pad;             // compute warps of the segment's CTA
+    int T, N, seg, K;       // K: columns per lane of the full warps
+    int W, pad;             // compute warps of the segment's CTA; pad: emission chunk (host path)
+    int KL, pad2;           // columns per lane of the last warp (its first lanes; the others hold KL-1)
 };
 
 struct Params {
@@ -147,12 +151,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
 }
 
-// token k (0-based) -> owning global lane / register slot: the first r global lanes hold K columns,
-// the rest K-1
-template <int K>
-__device__ __forceinline__ void owner_of(int k, int r, int &g, int &slot) {
-    if (K == 1 || k < r * K) { g = k / K; slot = k - g * K; }
-    else { const int kk = k - r * K; const int q = kk / (K > 1 ? K - 1 : 1); g = r + q; slot = kk - q * (K - 1); }
+// token k (0-based) -> owning global lane (32*warp + lane) and register slot, for a segment of N tokens laid out
+// as described at the top of this file
+__device__ __forceinline__ void column_owner(int k, int N, int W, int K, int KL, int &g, int &slot) {
+    const int full = 32 * K * (W - 1);
+    if (k < full) { g = k / K; slot = k - g * K; return; }
+    const int kk = k - full;
+    const int rL = (N - full) - 32 * (KL - 1);          // lanes of the last warp that own KL columns
+    int l;
+    if (KL == 1 || kk < rL * KL) { l = kk / KL; slot = kk - l * KL; }
+    else { const int k2 = kk - rL * KL; const int q = k2 / (KL - 1); l = rL + q; slot = k2 - q * (KL - 1); }
+    g = 32 * (W - 1) + l;
 }
 
 // Register budget per thread: the recurrence keeps 3K values live (state, choice accumulators, token
@@ -161,6 +170,184 @@ __device__ __forceinline__ void owner_of(int k, int r, int &g, int &slot) {
 #ifndef WXB_REGS
 #define WXB_REGS(K) ((K) <= 4 ? 40 : (K) <= 6 ? 56 : 64)
 #endif
+
+// One compute warp: the recurrence over its 32 lanes x KC columns, tile after tile behind its left neighbour.
+// KC = columns per lane of this warp; MIXED = the CTA's last warp (first r lanes hold KC columns, the rest KC-1,
+// and its last column is column N of the trellis); KF = columns per lane of the CTA's full warps (fixes the
+// warp's first column and the layout of the choice words).
+template <int KC, bool MIXED, bool DEBUG, bool WILD>
+__device__ __forceinline__ void compute_warp(const Params &p, const SegDesc &d, const SmemLayout &L, const uint32_t sm_base,
+                                             const int NB, const int TE, const int ntiles, const int wi, const int lane,
+                                             const int W, const int KF) {
+    const int T = d.T, N = d.N, V = p.V;
+    const uint32_t bar_tma = sm_base + L.off_bar;
+    const uint32_t bar_full = bar_tma + 8u * NB;
+    const uint32_t bar_empty = bar_full + 8u * NB;
+    const uint32_t bar_edge = bar_empty + 8u * NB;     // [w][b], w = 0..W-1 (row 0 unused)
+    const uint32_t left_stride_w = static_cast<uint32_t>(NB) * TE * 4u;   // bytes between left[w] and left[w+1]
+    // columns of this warp: [col0w, col0w + 32 KC) for a full warp; the last (MIXED) warp holds the m columns
+    // that remain, KC in its first r lanes and KC-1 in the others
+    const int col0w = wi * 32 * KF;
+    const int m = N - col0w;
+    const int r = MIXED ? m - 32 * (KC - 1) : 32;   // 1..32
+    const bool wide = !MIXED || lane < r;
+    const int cb = col0w + (wide ? lane * KC : r * KC + (lane - r) * (KC - 1));
+    const int ncols = wide ? KC : KC - 1;
+    const bool last_warp = MIXED;
+    // lane of this warp whose last real column is the warp's last column (KC = 1: the last warp may
+    // end before lane 31); in the last warp that column is column N of the trellis
+    const int laneN = (KC == 1 && MIXED) ? (m - 1) : 31;
+
+    uint32_t tokoff[KC];
+    uint32_t wmask = 0u;            // (WILD) bit i: column i is a wildcard token
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+        // byte offsets (token*4) come pre-multiplied from the plan: LDS [R + UR] with a uniform row base
+        const int t4 = (i < ncols) ? __ldg(p.tok4 + d.tok_base + cb + i) : 0;
+        if (WILD && t4 < 0) wmask |= 1u << i;
+        tokoff[i] = (t4 < 0) ? 0u : static_cast<uint32_t>(t4);
+    }
+    float R[KC];
+    uint32_t acc[KC];
+#pragma unroll
+    for (int i = 0; i < KC; ++i) { R[i] = -INFINITY; acc[i] = 0u; }   // trellis[0, 1:] = -inf  (:369)
+    float src = -INFINITY;          // this lane's last real column at the current row
+    const uint32_t rowstep = static_cast<uint32_t>(V) * 4u;
+    const uint32_t left_in0 = sm_base + L.off_left + wi * left_stride_w;      // left[wi][b][tt]
+    const uint32_t wait_bar0 = (wi == 0) ? bar_full : bar_edge + 8u * NB * wi;
+    const uint32_t next_bar0 = last_warp ? bar_empty : bar_edge + 8u * NB * (wi + 1);
+    uint32_t *bits_w = p.bits + d.bits_off + (static_cast<long long>(wi) * KF) * 32 + lane;   // next word to flush
+    const int bits_step = W * KF * 32;                                         // words per 32 frames
+
+    int t = 0;                      // frames consumed so far == current trellis row
+    int b = -1;                     // ring position and lap parity of the current tile
+    uint32_t ph = 0;
+    // Trellis column j is -inf in every row t < j (:369), so until frame `first column of this warp`
+    // all of the warp's cells are -inf and all of its choice bits 0 (-inf > -inf is false): whole
+    // tiles below that frame are passed on without running the recurrence.
+    const int skip_tiles = DEBUG ? 0 : min(col0w / TE, ntiles);
+    int tau = 0;
+    for (; tau < skip_tiles; ++tau) {
+        ++b;
+        const bool wrap = (b == NB);
+        b = wrap ? 0 : b;
+        ph ^= wrap ? 1u : 0u;
+        const int n = min(TE, T - tau * TE);
+        mbar_wait(wait_bar0 + 8u * b, ph);
+        if (lane < n) sts_f32(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * 4u, -INFINITY);
+        t += n;
+        if ((t & 31) == 0) {            // a 32-frame choice word is complete: all zeros
+#pragma unroll
+            for (int i = 0; i < KC; ++i) bits_w[i * 32] = 0u;
+            bits_w += bits_step;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(next_bar0 + 8u * b);
+    }
+    for (; tau < ntiles; ++tau) {
+        // branch-free ring step: a select keeps b / ph (and every address derived from them) in
+        // uniform registers, an `if` does not
+        ++b;
+        const bool wrap = (b == NB);
+        b = wrap ? 0 : b;
+        ph ^= wrap ? 1u : 0u;
+        const int n = min(TE, T - tau * TE);
+        mbar_wait(wait_bar0 + 8u * b, ph);
+
+        uint32_t rowaddr = sm_base + b * L.tile_bytes;
+        uint32_t left_in = left_in0 + static_cast<uint32_t>(b * TE) * 4u;     // advances with the tile
+        uint32_t left_out = left_in + left_stride_w;
+        uint32_t eb_in = sm_base + L.off_eb + static_cast<uint32_t>(b * TE) * 4u;
+        uint32_t wild_in = sm_base + L.off_wild + static_cast<uint32_t>(b * TE) * 4u;
+        asm volatile("" : "+r"(left_in), "+r"(left_out), "+r"(eb_in));   // materialise once per tile, not per frame under a predicate
+
+        // ---- the recurrence (:372-378): one frame ----
+        // eb = logp[t, blank]; lv = trellis[t, first column of this warp - 1] (used by lane 0); wv = wildcard emission
+        auto step = [&](float eb, float lv, float wv) {
+            float left = __shfl_up_sync(FULL, src, 1);
+            if (lane == 0) left = lv;
+            // chg first (it reads the *old* left neighbours), then stay / sign-difference as packed
+            // f32x2 adds (FADD2 on sm_100: one issue slot for two cells; IEEE round-to-nearest per lane)
+            float chg[KC];
+#pragma unroll
+            for (int i = KC - 1; i >= 0; --i) {
+                float e = lds_f32(rowaddr + tokoff[i]);
+                if (WILD && ((wmask >> i) & 1u)) e = wv;
+                chg[i] = ((i == 0) ? left : R[i - 1]) + e;    // trellis[t, j-1] + emission[t, tokens[j-1]]
+            }
+#pragma unroll
+            for (int i = 0; i + 1 < KC; i += 2) {
+                const float2 st = __fadd2_rn(make_float2(R[i], R[i + 1]), make_float2(eb, eb));   // trellis[t, j] + emission[t, blank]
+                const float2 dd = __fadd2_rn(st, make_float2(-chg[i], -chg[i + 1]));             // sign set <=> chg > stay (strict)
+                R[i] = fmax_nan(st.x, chg[i]);
+                R[i + 1] = fmax_nan(st.y, chg[i + 1]);
+                acc[i] = __funnelshift_l(__float_as_uint(dd.x), acc[i], 1);
+                acc[i + 1] = __funnelshift_l(__float_as_uint(dd.y), acc[i + 1], 1);
+            }
+            if (KC & 1) {
+                const float stay = R[KC - 1] + eb;
+                const float dd = stay - chg[KC - 1];
+                R[KC - 1] = fmax_nan(stay, chg[KC - 1]);
+                acc[KC - 1] = __funnelshift_l(__float_as_uint(dd), acc[KC - 1], 1);
+            }
+            rowaddr += rowstep;
+            ++t;
+            if (KC >= 2 && MIXED) src = wide ? R[KC - 1] : R[(KC >= 2) ? KC - 2 : 0];
+            else src = R[KC - 1];
+            if (DEBUG) {
+                float *tr = p.trellis + d.trellis_off + static_cast<long long>(t) * (N + 1);
+#pragma unroll
+                for (int i = 0; i < KC; ++i)
+                    if (i < ncols) tr[1 + cb + i] = R[i];
+                if (p.final_col && last_warp && lane == laneN) p.final_col[d.frame_base + d.seg + t] = src;
+            }
+        };
+        auto flush_if_word_done = [&]() {
+            if ((t & 31) == 0) {
+#pragma unroll
+                for (int i = 0; i < KC; ++i) bits_w[i * 32] = acc[i];
+                bits_w += bits_step;
+            }
+        };
+
+        // four frames at a time: their blank log-probs and left-boundary values arrive as one float4 each,
+        // and the four rows of this warp's last column leave as one float4 (LSU instructions, not issue
+        // slots, are the scarcest resource of this loop: profiles/r1_occupancy_and_pipes.md)
+        int tt = 0;
+        for (; tt + UNR <= n; tt += UNR) {
+            const float4 e4 = lds_f32x4(eb_in);
+            const float4 l4 = lds_f32x4(left_in);
+            float4 w4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (WILD) w4 = lds_f32x4(wild_in);
+            const float s0 = src; step(e4.x, l4.x, w4.x);
+            const float s1 = src; step(e4.y, l4.y, w4.y);
+            const float s2 = src; step(e4.z, l4.z, w4.z);
+            const float s3 = src; step(e4.w, l4.w, w4.w);
+            if (lane == laneN) sts_f32x4(left_out, s0, s1, s2, s3);    // rows t..t+3 of my last column -> warp wi+1
+            eb_in += 16u; left_in += 16u; left_out += 16u; wild_in += 16u;
+        }
+        for (; tt < n; ++tt) {             // the last, partial block of a segment
+            const float eb = lds_f32(eb_in), lv = lds_f32(left_in);
+            const float wv = WILD ? lds_f32(wild_in) : 0.0f;
+            if (lane == laneN) sts_f32(left_out, src);
+            step(eb, lv, wv);
+            eb_in += 4u; left_in += 4u; left_out += 4u; wild_in += 4u;
+        }
+        // tiles are 32, 16, 8 or 4 frames long and start at multiples of their length: a 32-frame choice word
+        // can only end where a tile ends, so the check sits here and not in the frame loop (six predicated
+        // instructions per four frames otherwise)
+        flush_if_word_done();
+        __syncwarp();
+        // hand the tile on: boundary values to warp wi+1, or the buffer back to the producer
+        if (lane == 0) mbar_arrive(next_bar0 + 8u * b);
+    }
+    if (t & 31) {   // last, partial word: left-align so that frame t' sits at bit 31-(t'%32)
+        const int sh = 32 - (t & 31);
+#pragma unroll
+        for (int i = 0; i < KC; ++i) bits_w[i * 32] = acc[i] << sh;
+    }
+    if (last_warp && lane == laneN) sts_f32(sm_base + L.off_fin, src);      // trellis[T, N]
+}
 
 // WILD: the batch contains wildcard tokens (id -1, an extension over the reference — see DESIGN.md):
 // their emission at frame t is max over non-blank v of logp[t, v]; the producer computes it per frame
@@ -365,169 +552,20 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
         while (st0 < T) scan_next();    // the tiles still in flight when the last one was issued
         t_start = bestt;
         best_val = best;
+    } else if (wi < W - 1) {
+        compute_warp<K, false, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K);
     } else {
-        // ================================================================ compute warp wi
-        const int g = wi * 32 + lane;                   // global lane
-        const int r = N - 32 * W * (K - 1);             // 1..32W by construction of the (K, W) bucket
-        const bool wide = g < r;
-        const int cb = wide ? g * K : r * K + (g - r) * (K - 1);
-        const int ncols = wide ? K : K - 1;
-        const bool last_warp = (wi == W - 1);
-        // lane of this warp whose last real column is the warp's last column (K = 1: the last warp may
-        // end before lane 31); in the last warp that column is column N of the trellis
-        const int laneN = (K == 1 && last_warp) ? (N - 1 - 32 * (W - 1)) : 31;
-
-        uint32_t tokoff[K];
-        uint32_t wmask = 0u;            // (WILD) bit i: column i is a wildcard token
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            // byte offsets (token*4) come pre-multiplied from the plan: LDS [R + UR] with a uniform row base
-            const int t4 = (i < ncols) ? __ldg(p.tok4 + d.tok_base + cb + i) : 0;
-            if (WILD && t4 < 0) wmask |= 1u << i;
-            tokoff[i] = (t4 < 0) ? 0u : static_cast<uint32_t>(t4);
+        // the last warp: its own column count (warp-uniform switch; every case is the same loop for another KC)
+        switch (d.KL) {
+            case 1: compute_warp<1, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
+            case 2: if constexpr (K >= 2) compute_warp<2, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
+            case 3: if constexpr (K >= 3) compute_warp<3, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
+            case 4: if constexpr (K >= 4) compute_warp<4, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
+            case 5: if constexpr (K >= 5) compute_warp<5, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
+            case 6: if constexpr (K >= 6) compute_warp<6, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
+            case 7: if constexpr (K >= 7) compute_warp<7, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
+            default: if constexpr (K >= 8) compute_warp<8, true, DEBUG, WILD>(p, d, L, sm_base, NB, TE, ntiles, wi, lane, W, K); break;
         }
-        float R[K];
-        uint32_t acc[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) { R[i] = -INFINITY; acc[i] = 0u; }   // trellis[0, 1:] = -inf  (:369)
-        float src = -INFINITY;          // this lane's last real column at the current row
-        const uint32_t rowstep = static_cast<uint32_t>(V) * 4u;
-        const uint32_t left_in0 = sm_base + L.off_left + wi * left_stride_w;      // left[wi][b][tt]
-        const uint32_t wait_bar0 = (wi == 0) ? bar_full : bar_edge + 8u * NB * wi;
-        const uint32_t next_bar0 = last_warp ? bar_empty : bar_edge + 8u * NB * (wi + 1);
-        uint32_t *bits_w = p.bits + d.bits_off + (static_cast<long long>(wi) * K) * 32 + lane;   // next word to flush
-        const int bits_step = W * K * 32;                                          // words per 32 frames
-
-        int t = 0;                      // frames consumed so far == current trellis row
-        int b = -1;                     // ring position and lap parity of the current tile
-        uint32_t ph = 0;
-        // Trellis column j is -inf in every row t < j (:369), so until frame `first column of this warp`
-        // all of the warp's cells are -inf and all of its choice bits 0 (-inf > -inf is false): whole
-        // tiles below that frame are passed on without running the recurrence.
-        const int g0 = wi * 32;
-        const int col0w = (g0 < r) ? g0 * K : r * K + (g0 - r) * (K - 1);
-        const int skip_tiles = DEBUG ? 0 : min(col0w / TE, ntiles);
-        int tau = 0;
-        for (; tau < skip_tiles; ++tau) {
-            ++b;
-            const bool wrap = (b == NB);
-            b = wrap ? 0 : b;
-            ph ^= wrap ? 1u : 0u;
-            const int n = min(TE, T - tau * TE);
-            mbar_wait(wait_bar0 + 8u * b, ph);
-            if (lane < n) sts_f32(left_in0 + left_stride_w + static_cast<uint32_t>(b * TE + lane) * 4u, -INFINITY);
-            t += n;
-            if ((t & 31) == 0) {            // a 32-frame choice word is complete: all zeros
-#pragma unroll
-                for (int i = 0; i < K; ++i) bits_w[i * 32] = 0u;
-                bits_w += bits_step;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(next_bar0 + 8u * b);
-        }
-        for (; tau < ntiles; ++tau) {
-            // branch-free ring step: a select keeps b / ph (and every address derived from them) in
-            // uniform registers, an `if` does not
-            ++b;
-            const bool wrap = (b == NB);
-            b = wrap ? 0 : b;
-            ph ^= wrap ? 1u : 0u;
-            const int n = min(TE, T - tau * TE);
-            mbar_wait(wait_bar0 + 8u * b, ph);
-
-            uint32_t rowaddr = sm_base + b * L.tile_bytes;
-            uint32_t left_in = left_in0 + static_cast<uint32_t>(b * TE) * 4u;     // advances with the tile
-            uint32_t left_out = left_in + left_stride_w;
-            uint32_t eb_in = sm_base + L.off_eb + static_cast<uint32_t>(b * TE) * 4u;
-            uint32_t wild_in = sm_base + L.off_wild + static_cast<uint32_t>(b * TE) * 4u;
-            asm volatile("" : "+r"(left_in), "+r"(left_out), "+r"(eb_in));   // materialise once per tile, not per frame under a predicate
-
-            // ---- the recurrence (:372-378): one frame ----
-            // eb = logp[t, blank]; lv = trellis[t, first column of this warp - 1] (used by lane 0); wv = wildcard emission
-            auto step = [&](float eb, float lv, float wv) {
-                float left = __shfl_up_sync(FULL, src, 1);
-                if (lane == 0) left = lv;
-                // chg first (it reads the *old* left neighbours), then stay / sign-difference as packed
-                // f32x2 adds (FADD2 on sm_100: one issue slot for two cells; IEEE round-to-nearest per lane)
-                float chg[K];
-#pragma unroll
-                for (int i = K - 1; i >= 0; --i) {
-                    float e = lds_f32(rowaddr + tokoff[i]);
-                    if (WILD && ((wmask >> i) & 1u)) e = wv;
-                    chg[i] = ((i == 0) ? left : R[i - 1]) + e;    // trellis[t, j-1] + emission[t, tokens[j-1]]
-                }
-#pragma unroll
-                for (int i = 0; i + 1 < K; i += 2) {
-                    const float2 st = __fadd2_rn(make_float2(R[i], R[i + 1]), make_float2(eb, eb));   // trellis[t, j] + emission[t, blank]
-                    const float2 dd = __fadd2_rn(st, make_float2(-chg[i], -chg[i + 1]));             // sign set <=> chg > stay (strict)
-                    R[i] = fmax_nan(st.x, chg[i]);
-                    R[i + 1] = fmax_nan(st.y, chg[i + 1]);
-                    acc[i] = __funnelshift_l(__float_as_uint(dd.x), acc[i], 1);
-                    acc[i + 1] = __funnelshift_l(__float_as_uint(dd.y), acc[i + 1], 1);
-                }
-                if (K & 1) {
-                    const float stay = R[K - 1] + eb;
-                    const float dd = stay - chg[K - 1];
-                    R[K - 1] = fmax_nan(stay, chg[K - 1]);
-                    acc[K - 1] = __funnelshift_l(__float_as_uint(dd), acc[K - 1], 1);
-                }
-                rowaddr += rowstep;
-                ++t;
-                if (K >= 2) src = wide ? R[K - 1] : R[(K >= 2) ? K - 2 : 0];
-                else src = R[0];
-                if (DEBUG) {
-                    float *tr = p.trellis + d.trellis_off + static_cast<long long>(t) * (N + 1);
-#pragma unroll
-                    for (int i = 0; i < K; ++i)
-                        if (i < ncols) tr[1 + cb + i] = R[i];
-                    if (p.final_col && last_warp && lane == laneN) p.final_col[d.frame_base + d.seg + t] = src;
-                }
-            };
-            auto flush_if_word_done = [&]() {
-                if ((t & 31) == 0) {
-#pragma unroll
-                    for (int i = 0; i < K; ++i) bits_w[i * 32] = acc[i];
-                    bits_w += bits_step;
-                }
-            };
-
-            // four frames at a time: their blank log-probs and left-boundary values arrive as one float4 each,
-            // and the four rows of this warp's last column leave as one float4 (LSU instructions, not issue
-            // slots, are the scarcest resource of this loop: profiles/r1_occupancy_and_pipes.md)
-            int tt = 0;
-            for (; tt + UNR <= n; tt += UNR) {
-                const float4 e4 = lds_f32x4(eb_in);
-                const float4 l4 = lds_f32x4(left_in);
-                float4 w4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (WILD) w4 = lds_f32x4(wild_in);
-                const float s0 = src; step(e4.x, l4.x, w4.x);
-                const float s1 = src; step(e4.y, l4.y, w4.y);
-                const float s2 = src; step(e4.z, l4.z, w4.z);
-                const float s3 = src; step(e4.w, l4.w, w4.w);
-                if (lane == laneN) sts_f32x4(left_out, s0, s1, s2, s3);    // rows t..t+3 of my last column -> warp wi+1
-                eb_in += 16u; left_in += 16u; left_out += 16u; wild_in += 16u;
-            }
-            for (; tt < n; ++tt) {             // the last, partial block of a segment
-                const float eb = lds_f32(eb_in), lv = lds_f32(left_in);
-                const float wv = WILD ? lds_f32(wild_in) : 0.0f;
-                if (lane == laneN) sts_f32(left_out, src);
-                step(eb, lv, wv);
-                eb_in += 4u; left_in += 4u; left_out += 4u; wild_in += 4u;
-            }
-            // tiles are 32, 16, 8 or 4 frames long and start at multiples of their length: a 32-frame choice word
-            // can only end where a tile ends, so the check sits here and not in the frame loop (six predicated
-            // instructions per four frames otherwise)
-            flush_if_word_done();
-            __syncwarp();
-            // hand the tile on: boundary values to warp wi+1, or the buffer back to the producer
-            if (lane == 0) mbar_arrive(next_bar0 + 8u * b);
-        }
-        if (t & 31) {   // last, partial word: left-align so that frame t' sits at bit 31-(t'%32)
-            const int sh = 32 - (t & 31);
-#pragma unroll
-            for (int i = 0; i < K; ++i) bits_w[i * 32] = acc[i] << sh;
-        }
-        if (last_warp && lane == laneN) *reinterpret_cast<float *>(sm + L.off_fin) = src;      // trellis[T, N]
     }
     __syncthreads();      // every warp's choice words (and trellis[T, N]) are visible to the walker
     if (wi != W) return;  // the producer warp holds the arg-max and walks back

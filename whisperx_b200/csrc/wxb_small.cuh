@@ -48,14 +48,10 @@ __global__ void __launch_bounds__(128) backtrack_kernel(const Params p, const in
     const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (idx >= count) return;
     const SegDesc db = p.segs[seg_first + idx];
-    const int K = db.K, W = db.W;
+    const int K = db.K, W = db.W, KL = db.KL;
     const int t_start = p.nframes[db.seg];
-    const int r = db.N - 32 * W * (K - 1);
     const long long wstep = static_cast<long long>(W) * K * 32;
-    auto owner = [&](int k, int &g, int &slot) {     // token k -> global lane / register slot (see align_kernel)
-        if (K == 1 || k < r * K) { g = k / K; slot = k - g * K; }
-        else { const int kk = k - r * K; const int q = kk / (K - 1); g = r + q; slot = kk - q * (K - 1); }
-    };
+    auto owner = [&](int k, int &g, int &slot) { column_owner(k, db.N, W, K, KL, g, slot); };     // token k -> global lane / register slot
     int status = 0;
     if (t_start == 0) {
         status = 1;                                  // empty walk -> for/else -> None
