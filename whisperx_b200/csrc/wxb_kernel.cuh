@@ -132,7 +132,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Blocks until the barrier's phase `parity` has completed.  try_wait suspends the thread in hardware until the
+// phase flips or a time limit expires; with the default (short, implementation-defined) limit the retry loop
+// of the waiting warps — producers ahead of their ring, compute warps behind their neighbour — was 17.6 % of all
+// instructions the kernel issued (ncu source view, profiles/r2_align_kernel_lines.md).  With an explicit limit of
+// 10 ms (the value CUTLASS passes) a waiting warp costs no issue slots; it still wakes as soon as the phase flips.
+#ifndef WXB_WAIT_HINT_NS
+#define WXB_WAIT_HINT_NS 0x989680u      // experiments: -DWXB_WAIT_HINT_NS=1u restores (nearly) the default behaviour
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if WXB_WAIT_HINT_NS
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(WXB_WAIT_HINT_NS) : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -142,6 +161,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -463,6 +483,8 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             return false;
         };
 
+        // (a single loop with one call site of issue() — step s issues tile s and processes tile s-1 — is 7 % slower
+        // on the benchmark batch: measured A/B, profiles/r2_ablation.md)
         bool cur_bulk = (ntiles > 0) ? issue(0) : false;
         int b = -1;
         uint32_t ph = 0;
@@ -502,15 +524,22 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
             if (lane < n) p.p0[d.frame_base + t0 + lane] = expf(e0);
             float mine_f = INFINITY;
             if (t0 < infstart) {
-                xd_s[lane] = static_cast<double>(e0);
+                xd_s[lane] = (lane < n) ? static_cast<double>(e0) : 0.0;
                 __syncwarp();
-                double mine = 0.0;
-                for (int i = 0; i < n; ++i) {       // same chain in every lane; lane i keeps prefix i
-                    if (i == lane) mine = cum;
-                    cum += xd_s[i];
+                // the same sequential chain in every lane (torch.cumsum's order); prefix i is parked in shared memory
+                // (every lane stores the same value) and picked up by lane i afterwards
+                double *pre_s = xd_s;               // in place: addend i is read before prefix i overwrites it
+#pragma unroll 2
+                for (int i = 0; i < TE; i += 2) {
+                    const double2 x2 = *reinterpret_cast<const double2 *>(xd_s + i);
+                    pre_s[i] = cum;
+                    cum += x2.x;
+                    pre_s[i + 1] = cum;
+                    cum += x2.y;
                 }
                 __syncwarp();
-                if (t0 + lane < infstart) mine_f = static_cast<float>(mine);
+                if (t0 + lane < infstart) mine_f = static_cast<float>(pre_s[lane]);
+                __syncwarp();
             }
             float wild_wide = -INFINITY;
             const bool wild_coop = V > WIDE_V || (V & 1) == 0;      // rows too long for one lane, or all in the same banks

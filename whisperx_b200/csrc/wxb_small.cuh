@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) upload_kernel(uint4 *dst, const uint4 *sr
 // The walk needs one choice word per visited (column, 32-frame word) pair: ~N + T/32 *dependent*
 // loads if done naively.  Instead the warp fetches a window of 32 columns x 4 words (128 frames)
 // with 4 independent loads per lane and walks inside it on register shuffles; a new window is
-// fetched only when the path leaves the block: about max(N/32, T/128) dependent round trips per
+// fetched only when the path leaves the block: about max(N/32, T/96) dependent round trips per
 // segment.
 __global__ void __launch_bounds__(128) backtrack_kernel(const Params p, const int seg_first, const int count) {
     const int lane = threadIdx.x & 31;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) backtrack_kernel(const Params p, const in
     } else {
         int j = db.N;                                // current column (token j-1 is being located)
         int s = t_start - 1;                         // frame of the current point
-        int *cs_ptr = p.c_start + db.tok_base + (j - 1);     // where token j-1's entry frame goes
+        int *cs = p.c_start + db.tok_base;           // token k's entry frame goes to cs[k]
         bool more = true;
         while (more) {
             const int j0 = j;                        // window columns j0, j0-1, ..., j0-31
@@ -74,29 +74,29 @@ __global__ void __launch_bounds__(128) backtrack_kernel(const Params p, const in
                 if (w0 >= 2) wC = __ldcg(bp - 2 * wstep);
                 if (w0 >= 3) wD = __ldcg(bp - 3 * wstep);
             }
-            const int jmin = j0 - 31;                // leave the window below this column ...
-            const int smin = (w0 - 3) << 5;          // ... or below this frame
-            bool inside = true;
-            // One iteration per visited (column, word) pair, branch-free inside: either the token's
-            // entry frame is in this word (store it, move one column left) or the path stayed through
-            // the rest of the word (move to the previous word).
-            while (inside) {
-                const int dw = w0 - (s >> 5);        // 0..3 inside the window
-                const uint32_t lo = (dw & 1) ? wB : wA;
-                const uint32_t hi = (dw & 1) ? wD : wC;
-                const uint32_t mine = (dw & 2) ? hi : lo;
-                const uint32_t word = __shfl_sync(FULL, mine, j0 - j);
-                // bit (31 - f%32) is frame f; shift so that bit 0 = frame s, bit q = frame s-q
-                const uint32_t m = word >> (31 - (s & 31));
+            const int jmin = max(j0 - 31, 1);        // leave the window below this column ...
+            const int smin = max((w0 - 2) << 5, 0);  // ... or below this frame (the look-back needs word ws and ws-1)
+            int my_entry = -1;                       // entry frame of this lane's column, once the walk has passed it
+            // One iteration per token (or per 32 frames the path stayed): the choice bits of the current column for
+            // frames s, s-1, ..., s-31 are cut out of two neighbouring words with one funnel shift — bit q = frame
+            // s-q, whatever the word alignment of s — so the lowest set bit is the frame that entered the token.
+            // Entry frames stay in the lane that owns the column and leave as one coalesced store per window.
+            do {
+                const int dw = w0 - (s >> 5);        // 0..2 inside the window
+                const bool d1 = (dw == 1), d2 = (dw == 2);
+                const uint32_t lo = d2 ? wC : (d1 ? wB : wA);      // word holding frame s
+                const uint32_t hi = d2 ? wD : (d1 ? wC : wB);      // the 32 frames before it
+                const uint32_t mine = __funnelshift_r(lo, hi, 31 - (s & 31));    // bit (31 - f%32) of a word is frame f
+                const int src_lane = j0 - j;
+                const uint32_t m = __shfl_sync(FULL, mine, src_lane);
                 const bool found = (m != 0u);
                 const int sc = s - (__ffs(m) - 1);   // frame at which token j-1 was entered (if found)
-                if (found && lane == 0) *cs_ptr = sc;
-                cs_ptr -= found ? 1 : 0;
+                if (found && lane == src_lane) my_entry = sc;
                 j -= found ? 1 : 0;
-                s = found ? sc - 1 : (s & ~31) - 1;
-                more = (j > 0) && (s >= 0);
-                inside = more && (j >= jmin) && (s >= smin);
-            }
+                s = found ? sc - 1 : s - 32;
+            } while (j >= jmin && s >= smin);
+            if (my_entry >= 0) cs[c - 1] = my_entry;
+            more = (j > 0) && (s >= 0);
         }
         status = (j == 0) ? 0 : 1;                   // ran out of frames before reaching token 0 -> None
     }
