@@ -53,13 +53,14 @@ def full(tag, rep):
             ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
             ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM % of peak")]
-    out = [f"# {tag}: `ncu --set full --clock-control none` of one step's align_kernel launches", "",
-           "Each (warps, tokens-per-lane) class is one launch; under ncu they run one at a time (in the real step they",
-           "share the GPU), so occupancy and issue rate below are per class in isolation.", ""]
+    out = [f"# {tag}: `ncu --set full --clock-control none` of one step's launches (align_kernel, backtrack_kernel, finalize_kernel)", "",
+           "Each warps-per-segment class is one chain of three launches; under ncu they run one at a time (in the real step",
+           "the chains share the GPU), so occupancy and issue rate below are per launch in isolation.", ""]
     out.append("| kernel | block | grid | " + " | ".join(n for _, n in want) + " |")
     out.append("|---|---|---|" + "---|" * len(want))
     rd = wr = 0.0
     inst = 0.0
+    per_kernel = defaultdict(lambda: [0.0, 0.0, 0.0, 0.0])      # dram read, dram write, warp instructions, duration us
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     for r in data:
         name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "")
@@ -71,6 +72,15 @@ def full(tag, rep):
         rd += float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale.get(units[idx["dram__bytes_read.sum"]], 1.0)
         wr += float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * scale.get(units[idx["dram__bytes_write.sum"]], 1.0)
         inst += float(r[idx["smsp__inst_executed.sum"]].replace(",", ""))
+        base = re.sub(r"<.*", "", name).replace("wxb::", "")
+        pk = per_kernel[base]
+        pk[0] += float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale.get(units[idx["dram__bytes_read.sum"]], 1.0)
+        pk[1] += float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * scale.get(units[idx["dram__bytes_write.sum"]], 1.0)
+        pk[2] += float(r[idx["smsp__inst_executed.sum"]].replace(",", ""))
+        pk[3] += float(r[idx["gpu__time_duration.sum"]].replace(",", "")) * {"ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(units[idx["gpu__time_duration.sum"]], 1.0)
+    out += ["", "| kernel | dram read MB | dram write MB | warp instructions M | serialised duration us |", "|---|---|---|---|---|"]
+    for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][2]):
+        out.append(f"| `{k}` | {v[0] / 1e6:.1f} | {v[1] / 1e6:.1f} | {v[2] / 1e6:.1f} | {v[3]:.1f} |")
     out += ["", f"Step totals over these {len(data)} launches: dram read {rd / 1e6:.1f} MB + write {wr / 1e6:.1f} MB = "
                 f"{(rd + wr) / 1e6:.1f} MB; {inst / 1e6:.1f} M warp instructions "
                 f"(>= {inst / (148 * 4 * 1.965e9) * 1e6:.0f} µs at 4 issue slots/clk/SM, 1.965 GHz)."]
@@ -82,7 +92,10 @@ def full(tag, rep):
     out += ["", f"Warp-state samples of the largest launch ({big[idx['Block Size']]} x {big[idx['Grid Size']]}): " +
             ", ".join(f"{n} {100 * v / tot:.1f} %" for n, v in sorted(st, key=lambda x: -x[1])[:8]) + "."]
     open(os.path.join(ROOT, "profiles", f"{tag}_align_kernel.md"), "w").write("\n".join(out) + "\n")
-    json.dump({"dram_bytes_per_step": rd + wr, "dram_read": rd, "dram_write": wr, "warp_instructions_per_step": inst,
+    al = per_kernel.get("align_kernel", [0, 0, 0, 0])
+    json.dump({"dram_bytes_per_step": al[0] + al[1], "dram_read": al[0], "dram_write": al[1],
+               "dram_bytes_per_step_whole_chain": rd + wr, "warp_instructions_per_step": inst,
+               "warp_instructions_align_kernel": al[2], "per_kernel": {k: {"dram_read": v[0], "dram_write": v[1], "warp_instructions": v[2]} for k, v in per_kernel.items()},
                "launches": len(data), "source": f"profiles/{tag}_align_kernel.md (ncu --set full, {os.path.basename(rep)})"},
               open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 

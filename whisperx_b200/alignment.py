@@ -76,9 +76,26 @@ EMISSION_MODE = os.environ.get("WXB_EMISSION_MODE", "torch")
 # (wxb_exact_scores_host): every `score` of the returned dict is byte-identical to the reference's.
 # False: scores come from the kernels (CUDA expf: <= 1e-6 relative, rounded values may differ by 0.001).
 EXACT_SCORES = os.environ.get("WXB_EXACT_SCORES", "1") not in ("", "0")
-# >1: segments with the same number of samples share one wav2vec2 forward;
-# 1 keeps the reference's batch-1 forwards (alignment.py:215 has this as a TODO).
+# The emission forward (alignment.py:212-232; the reference runs it segment by segment, batch 1 — its line 215
+# carries the TODO).  It stays a PyTorch module; what this file decides is how segments share forwards:
+#   EMISSION_BATCH   > 1: up to that many segments per forward.  Segments with the same number of samples are
+#                    stacked as they are — no padding, so normalisation statistics are untouched and the only
+#                    difference from batch 1 is the GEMM / convolution algorithm cuDNN and cuBLAS pick for the
+#                    larger batch (logits differ in the last bits: measured in profiles/r2_emission_batching.json).
+#                    1 (default) keeps the reference's batch-1 forwards: bit-identical emissions.
+#   EMISSION_PAD     opt-in, needs EMISSION_BATCH > 1: segments whose lengths are within EMISSION_PAD_SLACK of the
+#                    longest one of a bucket are zero-padded to it and go through the model's own `lengths` /
+#                    `attention_mask` path.  Only for models whose feature extractor normalises per frame
+#                    ("layer_norm": large / XLSR checkpoints): padded samples then never reach a valid frame (the
+#                    convolutions are unpadded, the encoder zeroes padded frames and masks them in attention).
+#                    Refused for "group_norm" extractors (WAV2VEC2_ASR_BASE_960H): their first layer normalises over
+#                    time, so padding would change every frame — those segments keep their own forward.
+#   EMISSION_PRECISION "fp32" (default: what the reference computes), or opt-in "tf32" / "bf16" (tensor cores;
+#                    emissions then differ from the reference's at the 1e-3 level: outside the parity contract).
 EMISSION_BATCH = int(os.environ.get("WXB_EMISSION_BATCH", "1"))
+EMISSION_PAD = os.environ.get("WXB_EMISSION_PAD", "0") not in ("", "0")
+EMISSION_PAD_SLACK = float(os.environ.get("WXB_EMISSION_PAD_SLACK", "0.1"))
+EMISSION_PRECISION = os.environ.get("WXB_EMISSION_PRECISION", "fp32")
 # EXTENSION, off by default (the reference fork drops characters its model does not know,
 # alignment.py:159-161): keep them as wildcard tokens scored as the best non-blank symbol of each
 # frame, so that digits, symbols and foreign letters get timestamps too.
@@ -141,32 +158,107 @@ def _forward(model, model_type: str, wav: torch.Tensor, lengths):
     return out
 
 
+def frames_for_samples(n_samples: int) -> int:
+    """wav2vec2 frame count: conv strides 5 * 2^6 = 320, receptive field 400."""
+    return (max(n_samples, 400) - 400) // 320 + 1
+
+
+def pads_safely(model, model_type: str) -> bool:
+    """True when zero-padded samples cannot reach a valid frame: the feature extractor normalises per frame
+    (layer norm), not over time (group norm)."""
+    if model_type == "torchaudio":
+        try:
+            first = model.feature_extractor.conv_layers[0].layer_norm
+        except AttributeError:
+            return False
+        return first is not None and not isinstance(first, torch.nn.GroupNorm)
+    if model_type == "huggingface":
+        return getattr(getattr(model, "config", None), "feat_extract_norm", "group") == "layer"
+    return False
+
+
+class _precision:
+    """Context for the emission forward: fp32 (reference), tf32 or bf16 (opt-in, EMISSION_PRECISION)."""
+
+    def __enter__(self):
+        self.old = torch.backends.cuda.matmul.allow_tf32
+        self.cast = None
+        if EMISSION_PRECISION == "tf32":
+            torch.backends.cuda.matmul.allow_tf32 = True
+        elif EMISSION_PRECISION == "bf16":
+            self.cast = torch.autocast("cuda", dtype=torch.bfloat16)
+            self.cast.__enter__()
+        elif EMISSION_PRECISION != "fp32":
+            raise ValueError(f"WXB_EMISSION_PRECISION={EMISSION_PRECISION!r}: expected fp32, tf32 or bf16")
+        return self
+
+    def __exit__(self, *exc):
+        if self.cast is not None:
+            self.cast.__exit__(*exc)
+        torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
+def _forward_padded(model, model_type: str, wavs: list, device):
+    """One forward over segments of different lengths through the model's own padding path.
+    -> list of [T_i, V] float32 tensors (valid frames only)."""
+    n = [int(w.shape[-1]) for w in wavs]
+    batch = torch.zeros((len(wavs), max(n)), dtype=wavs[0].dtype)
+    for i, w in enumerate(wavs):
+        batch[i, :n[i]] = w
+    batch = batch.to(device)
+    if model_type == "torchaudio":
+        out, _ = model(batch, lengths=torch.as_tensor(n, device=device))
+    else:
+        mask = (torch.arange(max(n))[None, :] < torch.as_tensor(n)[:, None]).to(device=device, dtype=torch.long)
+        out = model(batch, attention_mask=mask).logits
+    return [out[i, :frames_for_samples(n[i])].float() for i in range(len(wavs))]
+
+
 def _emit(model, model_type: str, audio: torch.Tensor, jobs: list, device) -> list:
     """wav2vec2 forward for every runnable segment (alignment.py:212-232); logits stay on `device`.
-    jobs: [(f1, f2)] sample ranges.  Returns one [T, V] float32 tensor per job and the channel count."""
+    jobs: [(f1, f2)] sample ranges.  Returns one [T, V] float32 tensor per job."""
     outs: List[Optional[torch.Tensor]] = [None] * len(jobs)
-    with torch.inference_mode():
-        order = range(len(jobs))
-        groups: dict = {}
+    with torch.inference_mode(), _precision():
+        done = set()
         if EMISSION_BATCH > 1 and audio.shape[0] == 1:
-            for i in order:
-                f1, f2 = jobs[i]
+            length = {}
+            for i, (f1, f2) in enumerate(jobs):
                 n = min(f2, audio.shape[1]) - f1
                 if n >= 400:
-                    groups.setdefault(n, []).append(i)
-        batched = set()
-        for n, members in groups.items():
-            for k in range(0, len(members), EMISSION_BATCH):
-                part = members[k:k + EMISSION_BATCH]
-                if len(part) < 2:
-                    continue
-                wav = torch.stack([audio[0, jobs[i][0]:jobs[i][1]] for i in part]).to(device)
-                logits = _forward(model, model_type, wav, None)
-                for row, i in enumerate(part):
-                    outs[i] = logits[row].float()
-                    batched.add(i)
-        for i in order:
-            if i in batched:
+                    length[i] = n
+            # 1. segments with the same number of samples: stacked, no padding (any model)
+            groups: dict = {}
+            for i, n in length.items():
+                groups.setdefault(n, []).append(i)
+            for n, members in groups.items():
+                for k in range(0, len(members), EMISSION_BATCH):
+                    part = members[k:k + EMISSION_BATCH]
+                    if len(part) < 2:
+                        continue
+                    wav = torch.stack([audio[0, jobs[i][0]:jobs[i][0] + n] for i in part]).to(device)
+                    logits = _forward(model, model_type, wav, None)
+                    for row, i in enumerate(part):
+                        outs[i] = logits[row].float()
+                        done.add(i)
+            # 2. opt-in: length buckets, zero-padded through the model's lengths / attention-mask path
+            if EMISSION_PAD and pads_safely(model, model_type):
+                rest = sorted((i for i in length if i not in done), key=lambda i: -length[i])
+                k = 0
+                while k < len(rest):
+                    part = [rest[k]]
+                    floor = length[rest[k]] * (1.0 - EMISSION_PAD_SLACK)
+                    while k + len(part) < len(rest) and len(part) < EMISSION_BATCH and length[rest[k + len(part)]] >= floor:
+                        part.append(rest[k + len(part)])
+                    k += len(part)
+                    if len(part) < 2:
+                        continue
+                    res = _forward_padded(model, model_type, [audio[0, jobs[i][0]:jobs[i][0] + length[i]] for i in part], device)
+                    for i, r in zip(part, res):
+                        outs[i] = r
+                        done.add(i)
+        for i in range(len(jobs)):
+            if i in done:
                 continue
             f1, f2 = jobs[i]
             wav = audio[:, f1:f2]
