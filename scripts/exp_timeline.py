@@ -36,7 +36,7 @@ def main():
     print(f"rows={n} span={end.max():.1f} us  last begin={beg.max():.1f} us  last forward pass done={fwd.max():.1f} us  "
           f"first walk done={end.min():.1f} us")
     K, T = rows[:, 6], rows[:, 4]
-    Wn = np.array([eng._lib.wxb_segment_warps(int(x)) for x in rows[:, 5]])
+    Wn = -(-rows[:, 5] // (32 * np.maximum(K, 1)))            # compute warps of the segment's CTA: ceil(N / 32K)
     KW = Wn * 100 + K
     for kw in sorted(set(KW.tolist()), reverse=True):
         m = KW == kw
