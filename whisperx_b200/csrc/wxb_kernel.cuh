@@ -331,8 +331,8 @@ __device__ __forceinline__ void compute_warp(const Params &p, const SegDesc &d, 
         };
 
         // four frames at a time: their blank log-probs and left-boundary values arrive as one float4 each,
-        // and the four rows of this warp's last column leave as one float4 (LSU instructions, not issue
-        // slots, are the scarcest resource of this loop: profiles/r1_occupancy_and_pipes.md)
+        // and the four rows of this warp's last column leave as one float4 (the LSU pipe is the busiest one of
+        // this loop: profiles/r2_align_kernel_lines.md; a two-frame body with float2 exchanges is 2-4 % slower)
         int tt = 0;
         for (; tt + UNR <= n; tt += UNR) {
             const float4 e4 = lds_f32x4(eb_in);
