@@ -109,17 +109,13 @@ __device__ __forceinline__ float exp_nonpos(float d) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d * 1.4426950408889634f));
     return y;
 }
-#ifndef WXB_LSM_UNROLL
-#define WXB_LSM_UNROLL 4
-#endif
-constexpr int LSM_UNROLL = WXB_LSM_UNROLL;      // unroll factor of the per-symbol loops of the row log-softmax
+// (the per-symbol loops are left to the compiler's own unrolling: explicit factors 1 / 2 / 4 / 8 measured 17 / 10 / 4 /
+// 13 % slower on the benchmark step than its default — profiles/r2_ablation.md)
 template <class Load>
 __device__ __forceinline__ void row_lse(Load x, int V, float &m, float &ls) {
     float mx = x(0);
-#pragma unroll LSM_UNROLL
     for (int v = 1; v < V; ++v) mx = fmaxf(mx, x(v));
     float s = 0.0f;
-#pragma unroll LSM_UNROLL
     for (int v = 0; v < V; ++v) s += exp_nonpos(x(v) - mx);
     m = mx;
     ls = logf(s);

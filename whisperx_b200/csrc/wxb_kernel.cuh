@@ -507,7 +507,6 @@ __global__ void __maxnreg__((DEBUG || WILD) ? 64 : WXB_REGS(K)) align_kernel(con
                     float *row = tb + lane * V;
                     float m, ls;
                     row_lse([&](int v) { return row[v]; }, V, m, ls);
-#pragma unroll LSM_UNROLL
                     for (int v = 0; v < V; ++v) row[v] = logp_from(row[v], m, ls);
                     p.rowmax[d.frame_base + t0 + lane] = m;
                     p.rowlse[d.frame_base + t0 + lane] = ls;
