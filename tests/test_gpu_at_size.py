@@ -163,3 +163,22 @@ def test_overlapped_runs_equal_serial_runs(engine):
             assert torch.equal(getattr(serial[i], f).view(torch.uint8), getattr(got, f).view(torch.uint8)), (i, f)
     for p in plans:
         p.close()
+
+
+@pytest.mark.parametrize("kind", ["iid", "planted"])
+def test_fused_log_softmax_against_torch_log_softmax(engine, kind):
+    """The DP is bit-exact given identical log-probs; the fused mode (WXB_F_LOGITS) computes its own log-probs, which
+    differ from torch.log_softmax by a few ulp.  What a user of the fused mode sees, measured: the fraction of
+    characters whose frames differ from the pipeline the reference runs (torch.log_softmax on the device, then the
+    DP) — reported, and bounded at 0.1 % (measured on these inputs: 0; scripts/measure_divergence.py has the full
+    sizes and the CPU log-softmax as well)."""
+    b = synth.make_batch(1024, "c2", align_frames=4, kind=kind)
+    raw = torch.from_numpy(b.emissions).cuda()
+    spec = lambda logits: BatchSpec(frame_off=b.frame_off, frame_len=b.frame_len, tok_off=b.tok_off, tokens=b.tokens,
+                                    vocab=b.vocab, blank_id=b.blank, logits=logits)
+    fused = engine.align_batch(raw, spec(True))
+    ref = engine.align_batch(torch.log_softmax(raw, -1), spec(False))
+    err = float((engine.log_softmax(raw) - torch.log_softmax(raw, -1)).abs().max())
+    diff = ((fused.char_start != ref.char_start) | (fused.char_end != ref.char_end)).float().mean().item()
+    print(f"fused vs torch.log_softmax ({kind}): max |dlogp| {err:.2e}, characters with different frames {100 * diff:.4f} %")
+    assert err <= 2e-5 and diff <= 1e-3 and torch.equal(fused.status, ref.status)

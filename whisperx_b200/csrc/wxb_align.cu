@@ -1137,6 +1137,7 @@ extern "C" int wxb_align_host(wxb_ctx *c, const wxb_batch *bt, const float *emis
     if (oh->logprobs) { CUDA_TRY(c->h_f32[3].ensure(sT * V * 4)); od.logprobs = c->h_f32[3].as<float>(); }
 
     cudaStream_t st = c->main;
+    CUDA_TRY(cudaStreamWaitEvent(st, c->slot[0].done, 0));       // an overlapped run may still be using slot 0's scratch
     // results stream back per chunk when there is anything to run (see HostSink); otherwise in bulk below
     const bool stream_back = !pl->buckets.empty();
     HostSink sink{oh, bt->tok_off, bt->word_off, bt->frame_off};
