@@ -667,7 +667,8 @@ def run_ours(args):
     if rank == 0:
         ms_step = ms_total / args.steps
         dp = float(np.mean(dp_ms))
-        achieved = plan.alg_bytes / (dp * 1e-3) / 1e9
+        # the chain's average duration over the timed region of `value` (K overlapped steps between two CUDA events)
+        achieved = plan.alg_bytes / (ms_step * 1e-3) / 1e9
         h2d = host_em.numel() * 4 + batch.tokens.nbytes + batch.frame_off.nbytes + batch.tok_off.nbytes + batch.frame_len.nbytes
         d2h = sum(getattr(host_out, f).numel() * getattr(host_out, f).element_size() for f in D2H_FIELDS)
         traffic = ncu_traffic()
@@ -691,10 +692,11 @@ def run_ours(args):
                          "traffic": traffic.get("dram_bytes_per_step"), "traffic_whole_chain": traffic.get("dram_bytes_per_step_whole_chain"),
                          "peak_source": peak_src,
                          "kernel": "wxb::align_kernel<K,false,false> followed by its backtrack_kernel and finalize_kernel: one such chain per "
-                                   "(warps, tokens-per-lane) class, the chains run concurrently on side streams and are timed together "
-                                   "with CUDA events on the launching stream",
-                         "kernel_ms": dp, "algorithmic_bytes_per_step": int(plan.alg_bytes),
-                         "issue_slot_frac": (traffic.get("warp_instructions_per_step") / (148 * 4 * 1.965e9 * dp * 1e-3)
+                                   "warps-per-segment class, the chains run concurrently on side streams; kernel_ms = their average duration "
+                                   "per step over the timed region of `value` (CUDA events on the launching stream around K overlapped "
+                                   "steps); kernel_ms_one_step_in_flight = the chain alone, bracketed by events inside wxb_plan_run",
+                         "kernel_ms": ms_step, "kernel_ms_one_step_in_flight": dp, "algorithmic_bytes_per_step": int(plan.alg_bytes),
+                         "issue_slot_frac": (traffic.get("warp_instructions_per_step") / (148 * 4 * 1.965e9 * ms_step * 1e-3)
                                              if traffic.get("warp_instructions_per_step") else None),
                          "note": "algorithmic bytes = sum(4*T*V + 20*N) per step; traffic = ncu dram read+write summed over the "
                                  "step's launches (profiles/); the recurrence is issue-bound, not HBM-bound (DESIGN.md 4.1): "

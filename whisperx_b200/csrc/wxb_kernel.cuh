@@ -140,6 +140,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 #ifndef WXB_WAIT_HINT_NS
 #define WXB_WAIT_HINT_NS 0x989680u      // experiments: -DWXB_WAIT_HINT_NS=1u restores (nearly) the default behaviour
 #endif
+// (one out-of-line copy of this loop instead of ~20 inlined ones would save 4 KB of hot code, but the calls cost
+// 27 % of the step: measured, profiles/r2_ablation.md)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if WXB_WAIT_HINT_NS
     asm volatile(
