@@ -8,12 +8,13 @@
 //   merge_repeats          whisperx/alignment.py:438-454  (finalize_kernel: per-token start/end/mean prob)
 //   char timestamps        whisperx/alignment.py:252-264  (finalize_kernel: exact decimal rounding)
 //
-// CTA = W compute warps + 1 producer warp.  Warps 0 .. W-2 are "full": every lane owns K consecutive token
-// columns (K = ceil(N / 32 W0) <= 8 for the planner's first guess W0, then W = ceil(N / 32K)).  The last warp
-// holds the m = N - 32K(W-1) columns that remain (1 <= m <= 32K) with KL = ceil(m / 32) <= K columns per lane:
-// its first rL = m - 32(KL-1) lanes own KL columns, the others KL-1, so the last column of the transcript is
-// the last column of its last occupied lane.  The recurrence loop is instantiated per column count: a
-// transcript of 399 tokens runs as 160 + 160 + 96 column slots (K = 5, KL = 3) instead of 3 x 160.
+// CTA = W compute warps + 1 producer warp.  Every segment of a batch runs with the batch's K (one kernel
+// instantiation per batch: the instruction cache decides between a fast and a slow step here), W = ceil(N / 32K).
+// Warps 0 .. W-2 are "full": every lane owns K consecutive token columns.  The last warp holds the
+// m = N - 32K(W-1) columns that remain (1 <= m <= 32K) with KL = ceil(m / 32) <= K columns per lane: its first
+// rL = m - 32(KL-1) lanes own KL columns, the others KL-1, so the last column of the transcript is the last
+// column of its last occupied lane.  The recurrence loop is instantiated per column count: a transcript of 399
+// tokens runs as 192 + 192 + 32 column slots (K = 6, KL = 1) instead of 3 x 192.
 //
 //   producer warp   streams the segment's emission rows HBM -> shared memory exactly once, TE frames
 //                   per tile through a ring of NB buffers (one cp.async.bulk per tile, mbarrier
