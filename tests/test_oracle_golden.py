@@ -7,6 +7,9 @@ import pytest
 import torch
 
 from oracle import c_oracle, ref_port
+from tests.helpers import host_exp_matches_fixtures
+
+SAME_EXP = host_exp_matches_fixtures()       # this machine's torch CPU exp is the one that generated the fixtures
 
 
 def _cases(golden_dp):
@@ -59,15 +62,24 @@ def test_torch_port_path_merge_words_exact(golden_dp):
             continue
         assert [p.token_index for p in path] == a["ptok"].tolist()
         assert [p.time_index for p in path] == a["ptime"].tolist()
-        assert [p.score for p in path] == a["pscore"].tolist()          # same torch exp: bit-exact
+        if SAME_EXP:                                                     # same torch exp: bit-exact
+            assert [p.score for p in path] == a["pscore"].tolist()
+        else:                                                            # another MKL code path: 1 ulp of float32
+            np.testing.assert_allclose([p.score for p in path], a["pscore"], rtol=2e-7, atol=0)
         segs = ref_port.collapse_repeats(path, m["transcript"])
         assert [s.start for s in segs] == a["sstart"].tolist() and [s.end for s in segs] == a["send"].tolist()
-        assert [s.score for s in segs] == a["sscore"].tolist()
+        if SAME_EXP:
+            assert [s.score for s in segs] == a["sscore"].tolist()
+        else:
+            np.testing.assert_allclose([s.score for s in segs], a["sscore"], rtol=2e-7, atol=0)
         assert "".join(s.label for s in segs) == m["transcript"]
         words = ref_port.collapse_words(segs)
         assert [w.label for w in words] == m["words"]
         assert [w.start for w in words] == a["wstart"].tolist() and [w.end for w in words] == a["wend"].tolist()
-        assert [w.score for w in words] == a["wscore"].tolist()
+        if SAME_EXP:
+            assert [w.score for w in words] == a["wscore"].tolist()
+        else:
+            np.testing.assert_allclose([w.score for w in words], a["wscore"], rtol=2e-7, atol=0)
 
 
 def test_round3_is_python_round():
