@@ -634,10 +634,12 @@ def run_ours(args):
     configs = []
     if world == 1 and not args.no_configs:
         recs = align_api_configs(dev, args.steps)
-        c4 = synth.make_batch(args.c4_segments, "c4", align_frames=4)
-        rec4 = time_device_batch(eng, dev, c4, torch.from_numpy(c4.emissions).to(dev), max(3, args.steps // 2), 3, peak, 4)
-        rec4.update(id="c4", workload=f"BASELINE configs[3]: {args.c4_segments} segments of 40-60 s, vocab 100 (blank = last id), "
-                                       "500-2,000-char transcripts, raw logits in (log_softmax_kernel, then the recurrence on log-probs), iid N(0,9) logits")
+        em4, c4 = synth.device_c4_batch(np.arange(args.c4_segments), dev)
+        rec4 = time_device_batch(eng, dev, c4, em4, max(3, args.steps // 2), 3, peak, 4)
+        rec4.update(id="c4", workload=f"BASELINE configs[3]: {args.c4_segments:,} segments of 40-60 s, vocab 100 (blank = last id), "
+                                       "500-2,000-char transcripts, raw logits in (log_softmax_kernel, then the recurrence on log-probs), "
+                                       "iid N(0,9) logits generated on the device")
+        del em4
         em5, m5 = synth.device_sweep_batch(np.arange(nseg), dev, kind="iid")
         rec5 = time_device_batch(eng, dev, m5, em5, args.steps, 3, peak, args.parity)
         rec5.update(id="c5", workload=f"BASELINE configs[4] batch shape: {nseg:,} segments of 30 s, vocab 29, 399-char transcripts, raw logits in "
@@ -793,7 +795,7 @@ def main():
     ap.add_argument("--only-main", action="store_true", help="profiling runs: the resident main workload only")
     ap.add_argument("--sweep-hours", type=float, default=10000.0, help="audio-hours in the strong-scaling pool")
     ap.add_argument("--sweep-kind", default="planted", choices=["iid", "planted"])
-    ap.add_argument("--c4-segments", type=int, default=512)
+    ap.add_argument("--c4-segments", type=int, default=2048)
     ap.add_argument("--parity", type=int, default=16, help="segments of every timed batch compared with the CPU oracle")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's local CPU cores")
     ap.add_argument("--workload", default=WORKLOAD, choices=["c2", "c5", "c4"],

@@ -32,6 +32,20 @@ def test_sweep_generator_is_a_function_of_the_segment_id():
     assert abs(float(em.view(32, rows, 29)[:, :1499].std()) - 3.0) < 0.5
 
 
+def test_c4_device_generator_shapes():
+    em, m = synth.device_c4_batch(np.arange(40, 56), "cpu")
+    n = np.diff(m.tok_off)
+    rows = int(m.frame_off[1])
+    assert m.vocab == 100 and m.blank == 99 and rows % 4 == 0 and rows >= int(m.frame_len.max())
+    assert (n >= 500).all() and (n <= 2000).all() and (n <= m.frame_len).all()
+    assert (m.frame_len >= synth.frames_for(40.0)).all() and (m.frame_len <= synth.frames_for(60.0)).all()
+    assert m.tokens.min() >= 0 and m.tokens.max() <= 98 and (m.tokens[m.tok_off[1:] - 1] != 4).all()
+    e = em.view(16, rows, 100)
+    assert float(e[3, int(m.frame_len[3]):].abs().max()) == 0.0
+    em2, m2 = synth.device_c4_batch(np.array([45, 41]), "cpu")
+    assert torch.equal(em2.view(2, rows, 100)[0], e[5]) and int(m2.frame_len[1]) == int(m.frame_len[1])
+
+
 def test_make_ref_copy_is_byte_identical():
     """oracle/make_ref.py: the build-time copy of the reference modules (git-ignored) equals the checkout."""
     import hashlib

@@ -197,3 +197,52 @@ def device_sweep_batch(seg_ids, device, duration_s: float = 30.0, vocab: int = 2
                       np.arange(S + 1, dtype=np.int64) * N, tok.to(torch.int32).cpu().numpy().reshape(-1),
                       np.full(S, float(duration_s)), vocab, blank)
     return em.view(S * Tp, vocab), meta
+
+
+def device_c4_batch(seg_ids, device, vocab: int = 100, kind: str = "iid", seed: int = 4321):
+    """BASELINE configs[3] on the device: segments of 40-60 s, 500 .. min(2000, T) tokens, vocabulary `vocab` with the
+    blank at the last id (HF '<pad>' style) and separator id 4 — the shape of make_batch(config="c4"), generated by
+    the counter-based generator so that a GPU-filling batch (thousands of segments, gigabytes of logits) does not have
+    to be drawn on the host.  Every segment occupies Tmax_padded rows of the emission matrix (frame_len holds its real
+    length); rows beyond a segment's length are zero.  Returns (emissions [S * Tp, V] CUDA float32, SynthBatch)."""
+    import torch
+    dev = torch.device(device)
+    ids = torch.as_tensor(np.asarray(seg_ids, dtype=np.int64), device=dev)
+    S = int(ids.numel())
+    blank, sep = vocab - 1, 4
+    key = _mix64(ids * _i64(0x9E3779B97F4A7C15) + _i64(seed))
+    dur = 40.0 + 20.0 * _uniform24(_mix64(key + 1), 20).double()                       # U[40, 60) seconds
+    T = ((dur * SAMPLE_RATE).long() - 400) // 320 + 1
+    hi = torch.clamp(T, max=2000)
+    N = 500 + (_uniform24(_mix64(key + 2), 20).double() * (hi - 500 + 1).double()).long().clamp(max=hi - 500)
+    Tmax = frames_for(60.0)
+    Tp = Tmax + (-Tmax) % 4
+    Nmax = 2000
+    k = torch.arange(Nmax, device=dev, dtype=torch.int64)
+    ht = _mix64(key[:, None] + (k[None, :] + 1) * _i64(0xD1B54A32D192ED03))
+    letters = torch.tensor([v for v in range(vocab) if v != blank and v != sep], device=dev, dtype=torch.int64)
+    tok = letters[((ht >> 8) & 0x7FFFFFFF) % letters.numel()]
+    is_sep = ((ht >> 44) & 0xFFFF) < (0x10000 * 2 // 11)
+    is_sep[:, 0] = False
+    is_sep[:, 1:] &= ~is_sep[:, :-1]
+    tok = torch.where(is_sep, torch.full_like(tok, sep), tok)
+    last = (N - 1).clamp(min=0)
+    fix = tok.gather(1, last[:, None]) == sep                                          # no separator at the end of a transcript
+    tok.scatter_(1, last[:, None], torch.where(fix, letters[0].expand_as(fix), tok.gather(1, last[:, None])))
+    em = torch.zeros((S, Tp, vocab), dtype=torch.float32, device=dev)
+    e_idx = torch.arange(Tmax * vocab, device=dev, dtype=torch.int64)
+    step = max(1, (1 << 27) // (Tmax * vocab))
+    for a in range(0, S, step):
+        h = _mix64(key[a:a + step, None] ^ ((e_idx[None, :] + 1) * _i64(0xA0761D6478BD642F)))
+        z = torch.sqrt(-2.0 * torch.log(_uniform24(h, 40))) * torch.cos(6.283185307179586 * _uniform24(h, 12))
+        em[a:a + step, :Tmax] = (z * 3.0).view(-1, Tmax, vocab)
+    live = torch.arange(Tp, device=dev)[None, :] < T[:, None]
+    em *= live[:, :, None]
+    if kind != "iid":
+        raise ValueError("device_c4_batch generates iid logits only")
+    Th, Nh = T.cpu().numpy(), N.cpu().numpy()
+    tok_h = tok.to(torch.int32).cpu().numpy()
+    tokens = np.concatenate([tok_h[s, :Nh[s]] for s in range(S)]) if S else np.zeros(0, np.int32)
+    meta = SynthBatch(None, np.arange(S + 1, dtype=np.int64) * Tp, Th.astype(np.int32),
+                      np.concatenate([[0], np.cumsum(Nh)]).astype(np.int64), tokens, dur.cpu().numpy().astype(np.float64), vocab, blank)
+    return em.view(S * Tp, vocab), meta
