@@ -387,7 +387,7 @@ def align_api_configs(dev, steps):
         # ---- configs[2]: one hour, char-level alignment, wildcard tokens (extension, off by default)
         wxa.WILDCARD = True
         timed(segs[:4], audio[: 4 * 30 * 16000], 1, return_char_alignments=True)
-        s3, res3 = timed(segs, audio, 1, return_char_alignments=True)
+        s3, res3 = timed(segs, audio, 3, return_char_alignments=True)            # median of three whole-hour calls
         k = 3
         ref3 = ref_port.align_port(copy.deepcopy(segs[:k]), model, meta, audio[: k * 30 * 16000], str(dev), return_char_alignments=True,
                                    span_fn=spans, wildcard=True)
