@@ -102,6 +102,7 @@ EMISSION_PRECISION = os.environ.get("WXB_EMISSION_PRECISION", "fp32")
 WILDCARD = os.environ.get("WXB_WILDCARD", "0") not in ("", "0")
 # Introspection for the parity tests: when True, align() keeps the last batch it ran (spec, device
 # results and, in fused mode, the log-probs the kernels computed) in LAST_BATCH.
+TIMING = os.environ.get("WXB_ALIGN_TIMING", "0") not in ("", "0")     # per-stage wall times of align() on stderr
 KEEP_LAST_BATCH = False
 LAST_BATCH: dict = {}
 
@@ -322,8 +323,12 @@ def align_grouped(transcript, model, align_model_metadata, audio, device, interp
         raise NotImplementedError(f"Align model of type {model_type} not supported.")
 
     # 1. keep only characters the model knows (mutates the input, like the reference)
+    import time as _time
+    _t = [_time.perf_counter()]
+    _mark = (lambda: (torch.cuda.synchronize(dev), _t.append(_time.perf_counter()))) if TIMING else (lambda: None)
     transcript = transcript if isinstance(transcript, list) else list(transcript)
     assemble.prepare_transcript(transcript, dictionary, lang, print_progress, combined_progress, wildcard=WILDCARD)
+    _mark()
 
     # 2a. which segments reach the model (alignment.py:198-207)
     plain: List[dict] = []
@@ -346,7 +351,9 @@ def align_grouped(transcript, model, align_model_metadata, audio, device, interp
     if run:
         jobs = [(int(transcript[s]["start"] * SAMPLE_RATE), int(transcript[s]["end"] * SAMPLE_RATE)) for s in run]
         logits = _emit(model, model_type, audio, jobs, dev)
+        _mark()
         results = _align_batch(engine, [transcript[s] for s in run], logits, dictionary, lang, audio.shape[0])
+        _mark()
 
     # 3. records, in input order
     grouped: List[List[dict]] = []
@@ -365,6 +372,11 @@ def align_grouped(transcript, model, align_model_metadata, audio, device, interp
                 continue
         print(f'Failed to align segment ("{seg["text"]}"): {why}')
         grouped.append([plain[sdx]])
+    if TIMING and len(_t) == 4:
+        _mark()
+        import sys as _sys
+        print("[wxb] align(): text prep %.1f ms, emission forward %.1f ms, alignment batch (layout + kernels + exact scores) %.1f ms, "
+              "record assembly %.1f ms" % tuple((b - a) * 1e3 for a, b in zip(_t, _t[1:])), file=_sys.stderr)
     return grouped
 
 
