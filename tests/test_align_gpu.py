@@ -299,3 +299,37 @@ def test_huggingface_style_model_with_a_32_symbol_head(wxa, mode):
     wxa.KEEP_LAST_BATCH = False
     again = wxa.align(copy.deepcopy(TRANSCRIPT), model, meta, audio, "cuda:0", return_char_alignments=True)   # in-place route
     assert same_records(again["segments"], ours["segments"]) is None
+
+
+@pytest.mark.needs_reference
+def test_the_reference_itself_on_cuda_returns_the_same_dict(wxa):
+    """The drop-in claim, end to end: the *unmodified reference* `whisperx.alignment.align()` (imported from
+    /root/reference, or from its build-time copy oracle/_ref on the GPU box) and `whisperx_b200.align()` run on the same
+    random-init WAV2VEC2_ASR_BASE_960H, the same audio and the same transcript with device="cuda" must return the same
+    dict — text, timestamps and scores compared for equality, no tolerance (default settings: torch.log_softmax on the
+    device like the reference, scores finished with the host's exp like the reference) — and leave the same keys on
+    the input segments."""
+    from oracle import ref_import
+    A = ref_import.load_reference_alignment()
+    ref_import.set_sentence_splitter(regex_spans)
+    model = _random_model()
+    meta = {"language": "en", "dictionary": DICTIONARY, "type": "torchaudio"}
+    g = torch.Generator().manual_seed(11)
+    audio = (torch.randn(40 * 16000, generator=g) * 0.1).numpy()
+    transcript = TRANSCRIPT + [
+        {"start": 15.0, "end": 39.5, "text": "A much longer segment follows here, with several sentences in it. Some are short. Others go on for quite "
+                                             "a while before they stop! Does the question mark work? It should; and so should 3 numbers like 42 or 1999."},
+        {"start": 39.5, "end": 45.0, "text": "clipped by the end of the audio"},
+    ]
+    assert wxa.EMISSION_MODE == "torch" and wxa.EXACT_SCORES and wxa.EMISSION_BATCH == 1
+    for chars in (False, True):
+        ref_in, our_in = copy.deepcopy(transcript), copy.deepcopy(transcript)
+        ref = A.align(ref_in, model, meta, audio, "cuda:0", return_char_alignments=chars)
+        ours = wxa.align(our_in, model, meta, audio, "cuda:0", return_char_alignments=chars)
+        d = same_records(ours["segments"], ref["segments"], score_tol=0.0)
+        assert d is None, d
+        assert same_records(ours["word_segments"], ref["word_segments"], score_tol=0.0) is None
+        assert len(ours["segments"]) >= 10 and sum("start" in w for w in ours["word_segments"]) > 60
+        for a, b in zip(our_in, ref_in):
+            assert a["clean_char"] == b["clean_char"] and a["clean_cdx"] == b["clean_cdx"] and a["clean_wdx"] == b["clean_wdx"]
+            assert [tuple(x) for x in a["sentence_spans"]] == [tuple(x) for x in b["sentence_spans"]]
