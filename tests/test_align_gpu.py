@@ -333,3 +333,34 @@ def test_the_reference_itself_on_cuda_returns_the_same_dict(wxa):
         for a, b in zip(our_in, ref_in):
             assert a["clean_char"] == b["clean_char"] and a["clean_cdx"] == b["clean_cdx"] and a["clean_wdx"] == b["clean_wdx"]
             assert [tuple(x) for x in a["sentence_spans"]] == [tuple(x) for x in b["sentence_spans"]]
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("variant", ["ja_linear", "huggingface_32"])
+def test_the_reference_itself_on_cuda_other_paths(wxa, variant):
+    """Same statement as above for the paths the English torchaudio case does not take: a language without spaces
+    (every character its own word, alignment.py:22,277-278) with linear interpolation of un-alignable sentences, and a
+    HuggingFace-style model (`.logits`, 32-symbol head with '<pad>' as blank, alignment.py:229-230,237-240)."""
+    from oracle import ref_import
+    A = ref_import.load_reference_alignment()
+    ref_import.set_sentence_splitter(regex_spans)
+    g = torch.Generator().manual_seed(12)
+    audio = (torch.randn(20 * 16000, generator=g) * 0.1).numpy()
+    if variant == "ja_linear":
+        model, meta = _random_model(), {"language": "ja", "dictionary": DICTIONARY, "type": "torchaudio"}
+        transcript = [{"start": 0.0, "end": 6.0, "text": "abc de。12。fgh!ij k"}, {"start": 6.0, "end": 13.0, "text": " 99。lm nop? 7。qrs "},
+                      {"start": 13.0, "end": 19.0, "text": "tuv wxyz"}]
+        kw = dict(interpolate_method="linear", return_char_alignments=True)
+    else:
+        specials = ["<pad>", "<s>", "</s>", "<unk>", "|"]
+        vocab = {tok: i for i, tok in enumerate(specials + list("abcdefghijklmnopqrstuvwxyz") + ["'"])}
+        model, meta = _HFStyle(32).to("cuda:0"), {"language": "en", "dictionary": vocab, "type": "huggingface"}
+        transcript = copy.deepcopy(TRANSCRIPT)
+        kw = dict(return_char_alignments=True)
+    ref_in, our_in = copy.deepcopy(transcript), copy.deepcopy(transcript)
+    ref = A.align(ref_in, model, meta, audio, "cuda:0", **kw)
+    ours = wxa.align(our_in, model, meta, audio, "cuda:0", **kw)
+    d = same_records(ours["segments"], ref["segments"], score_tol=0.0)
+    assert d is None, d
+    assert same_records(ours["word_segments"], ref["word_segments"], score_tol=0.0) is None
+    assert sum("start" in w for w in ours["word_segments"]) >= 8
