@@ -547,3 +547,48 @@ def test_vocabulary_beyond_the_limit_is_refused(engine):
     E = torch.zeros((4, V), device="cuda")
     with pytest.raises(NativeError):
         engine.align_batch(E, BatchSpec(frame_off=[0, 4], tok_off=[0, 2], tokens=[1, 2], vocab=V))
+
+
+@pytest.mark.needs_reference
+def test_engine_against_the_reference_functions_live(engine):
+    """The reference's own get_trellis / backtrack / merge_repeats (unmodified whisperx/alignment.py, from /root/reference
+    or its build-time copy oracle/_ref) on this machine against the CUDA path on the same log-probs: random shapes incl.
+    N = T and N > T, blank != 0, quantised (tie-heavy) emissions.  Trellis and frames bit-exact; scores exact once the
+    path's log-probs go through the host's exp and the reference-order reductions (wxb_exact_scores_host)."""
+    import ctypes as C
+    from oracle import ref_import
+    from whisperx_b200 import _native as N
+    A = ref_import.load_reference_alignment()
+    rng = np.random.default_rng(2026)
+    cases, blanks = [], []
+    for i in range(24):
+        V = int(rng.choice([5, 29, 32, 100]))
+        T = int(rng.integers(2, 320))
+        Nn = int(rng.integers(1, T + 2)) if i % 5 else T
+        cases.append((logprobs(rng, T, V, ties=bool(i % 3 == 0)), rng.integers(0, V, Nn).astype(np.int32)))
+        blanks.append(V)
+    for V in sorted(set(blanks)):
+        sub = [c for c, v in zip(cases, blanks) if v == V]
+        blank = 0 if V == 29 else V - 1
+        spec, res = run(engine, sub, V, blank, align=4, want=("path", "trellis"), no_shortcut=True)
+        toff = spec.trellis_offsets()
+        prob = torch.exp(res.path_logp).contiguous()
+        score, score_r = np.empty(max(spec.sum_N, 1)), np.empty(max(spec.sum_N, 1))
+        cb = spec.to_c()
+        N.check(engine._lib.wxb_exact_scores_host(C.byref(cb), prob.data_ptr(), res.status.data_ptr(), res.char_start.data_ptr(),
+                                                  res.char_end.data_ptr(), score.ctypes.data, score_r.ctypes.data, None), "exact")
+        for s, (E, tk) in enumerate(sub):
+            Et = torch.from_numpy(E)
+            R = A.get_trellis(Et, tk.tolist(), blank)
+            mine = res.trellis[toff[s]:toff[s + 1]].view(R.shape)
+            assert torch.equal(mine.view(torch.int32), R.view(torch.int32)), (V, s)
+            path = A.backtrack(R, Et, tk.tolist(), blank)
+            sl = slice(int(spec.tok_off[s]), int(spec.tok_off[s + 1]))
+            if path is None:
+                assert int(res.status[s]) == 1
+                continue
+            segs = A.merge_repeats(path, "x" * len(tk))
+            assert int(res.status[s]) == 0
+            assert res.char_start[sl].tolist() == [g.start for g in segs] and res.char_end[sl].tolist() == [g.end for g in segs]
+            assert score[sl].tolist() == [g.score for g in segs]
+            np.testing.assert_allclose(res.char_score[sl].numpy(), [g.score for g in segs], rtol=SCORE_RTOL, atol=0)
