@@ -645,7 +645,7 @@ def run_ours(args):
         rec5.update(id="c5", workload=f"BASELINE configs[4] batch shape: {nseg:,} segments of 30 s, vocab 29, 399-char transcripts, raw logits in "
                                        "(fused log-softmax), iid N(0,9) logits generated on the device")
         del em5
-        configs = [recs[0], {"id": "c2", "see": "top level (value / value_planted / e2e)"}, recs[1], rec4, rec5]
+        configs = [recs[0], {"id": "c2", "see": "top level (value / value_serial / value_planted / e2e)"}, recs[1], rec4, rec5]
 
     # ---- BASELINE configs[4]: strong scaling over a fixed pool, through the sharder ----
     strong = None
@@ -721,6 +721,9 @@ def run_ours(args):
                                      "workload": "same segments, planted emissions (+8 on a random monotone token path, +8 on blank elsewhere): "
                                                  "full-length paths, the realistic case for backtrack_kernel / finalize_kernel"}
         if configs:
+            configs[1].update(workload=line["config"]["workload"], segments=nseg, ms_per_step=ms_step, value=line["value"], unit=UNIT,
+                              cells_per_s=line["cells_per_s"], hbm_frac=achieved / peak, failed_segments=failed,
+                              gpu_launches_per_step=int(plan.launches), parity_checked=int(units[8]))
             line["configs"] = configs
         if strong:
             hours = strong["n_pool"] / 120.0
